@@ -1,0 +1,318 @@
+"""oracle.py — Python face of the CPU restatement.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module;
+nothing under pmp-mcmc_b200/ does.  It wraps oracle/liboracle.so (pmp_oracle.c) and restates, in plain numpy loops that
+follow the reference line by line, the acceptance rules and the categorical draws:
+
+    mp_logweights        GMOptimizer.step         simple_net/lb.py:139-150   (500_MP.cu:22-31; error.py:58-64)
+    psp_logweights       preMOptimizer.step       simple_net/lb.py:206-240   (error.py:96-121, com_dim.py:44-68, PMP_FC.py:117-136)
+    pmp_logweights       GMpreOptimizerV2.step    simple_net/lb.py:304-330   (error.py:151-173)
+    table_logweights     CUDA PMP kernels         500_PMP.cu:23-30, conv_pmp.cu:22-33 (+ host tables 500_PMP.cu:180-193, conv_pmp.cu:198-218)
+    draw_numpy           pandas sample → RandomState.choice: cdf=cumsum(p); cdf/=cdf[-1]; searchsorted(cdf,u,'right')
+    draw_libstdcxx       std::discrete_distribution: p=w/sum; partial_sum; lower_bound   (500_MP.cu:218-222)
+    loglik_lb_torch      BayesNet.loglik          simple_net/lb.py:103-108 (torch float32, as the reference runs it)
+
+Pinning status: see the header of pmp_oracle.c and tests/golden/README.md.
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    """Compile liboracle.so (and oracle/_ref when /root/reference is mounted)."""
+    subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "pmp_oracle.c")):
+            subprocess.run(["make", "-C", _HERE, "--no-print-directory", "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+        L = ctypes.CDLL(path)
+        u64, u32, i64, dbl = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, ctypes.c_double
+        fp = ctypes.POINTER(ctypes.c_float)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.oracle_stream_u64.restype = u64
+        L.oracle_stream_u64.argtypes = [u64, u64, u32, u64]
+        L.oracle_stream_normal.restype = dbl
+        L.oracle_stream_normal.argtypes = [u64, u64, u32, u64]
+        L.oracle_norm_ppf.restype = dbl
+        L.oracle_norm_ppf.argtypes = [dbl]
+        L.oracle_det_log.restype = dbl
+        L.oracle_det_log.argtypes = [dbl]
+        L.oracle_stream_normals.argtypes = [u64, u64, u32, u64, i64, dp]
+        L.oracle_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, dp]
+        L.oracle_philox4x32_10.argtypes = [ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]
+        L.oracle_propose.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, fp, u64, u64, fp]
+        L.oracle_loglik_linear_refcuda.argtypes = [fp, fp, i64, fp, ctypes.c_int, dbl, fp]
+        L.oracle_loglik_linear_f64.argtypes = [fp, fp, i64, fp, ctypes.c_int, dbl, dp]
+        L.oracle_loglik_linear_suffstat.argtypes = [fp, fp, i64, fp, ctypes.c_int, dbl, dp]
+        L.oracle_sumsq_fixed_mirror.argtypes = [fp, fp, i64, fp, ctypes.c_int, i64, ctypes.POINTER(u64)]
+        L.oracle_blocked_cdf.argtypes = [dp, ctypes.c_int, dp]
+        _LIB = L
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+STREAM_PROPOSAL, STREAM_DRAW, STREAM_PICK, STREAM_CHAIN_INIT = 0, 1, 2, 3
+TREE_FLAT, TREE_BINARY, TREE_BARY = 0, 1, 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# streams
+def philox4x32_10(ctr, key):
+    c = (ctypes.c_uint32 * 4)(*ctr)
+    k = (ctypes.c_uint32 * 2)(*key)
+    o = (ctypes.c_uint32 * 4)()
+    lib().oracle_philox4x32_10(c, k, o)
+    return [int(v) for v in o]
+
+
+def stream_normals(seed, it, stream, idx0, count):
+    out = np.empty(count, dtype=np.float64)
+    lib().oracle_stream_normals(seed, it, stream, idx0, count, _dptr(out))
+    return out
+
+
+def stream_uniforms(seed, it, stream, idx0, count):
+    out = np.empty(count, dtype=np.float64)
+    lib().oracle_stream_uniforms(seed, it, stream, idx0, count, _dptr(out))
+    return out
+
+
+def num_nodes(tree, b, depth):
+    return b if tree == TREE_FLAT else (2 ** depth if tree == TREE_BINARY else b ** depth)
+
+
+def propose(tree, b, depth, dim, alpha, state, seed, it):
+    P = num_nodes(tree, b, depth)
+    st = _f32(state)
+    out = np.empty((P, dim), dtype=np.float32)
+    lib().oracle_propose(tree, b, depth, dim, ctypes.c_float(alpha), _fptr(st), seed, it, _fptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# linear-Gaussian sweep
+def loglik_linear_refcuda(x, y, nets, scale):
+    x, y, nets = _f32(x), _f32(y), _f32(nets)
+    out = np.zeros(nets.shape[0], dtype=np.float32)
+    lib().oracle_loglik_linear_refcuda(_fptr(x), _fptr(y), x.size, _fptr(nets), nets.shape[0], scale, _fptr(out))
+    return out
+
+
+def loglik_linear_f64(x, y, nets, scale):
+    x, y, nets = _f32(x), _f32(y), _f32(nets)
+    out = np.zeros(nets.shape[0], dtype=np.float64)
+    lib().oracle_loglik_linear_f64(_fptr(x), _fptr(y), x.size, _fptr(nets), nets.shape[0], scale, _dptr(out))
+    return out
+
+
+def loglik_linear_suffstat(x, y, nets, scale):
+    x, y, nets = _f32(x), _f32(y), _f32(nets)
+    out = np.zeros(nets.shape[0], dtype=np.float64)
+    lib().oracle_loglik_linear_suffstat(_fptr(x), _fptr(y), x.size, _fptr(nets), nets.shape[0], scale, _dptr(out))
+    return out
+
+
+def sumsq_fixed_mirror(x, y, nets, total_chunks_for_limit):
+    x, y, nets = _f32(x), _f32(y), _f32(nets)
+    out = np.zeros(nets.shape[0], dtype=np.uint64)
+    lib().oracle_sumsq_fixed_mirror(_fptr(x), _fptr(y), x.size, _fptr(nets), nets.shape[0], total_chunks_for_limit,
+                                    out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    return out
+
+
+def loglik_linear_from_fixed(acc, nets, n_global, scale):
+    """log-target from the integer sums, as csrc/accept.cuh finalises them."""
+    sg = _f32(nets)[:, 2].astype(np.float64)
+    S = acc.astype(np.int64).astype(np.float64) / float(1 << 20)
+    return (-0.5 * n_global * np.log(6.283185307179586477 * sg * sg) - 0.5 * S) / scale
+
+
+def loglik_lb_torch(x, y, nets, threads=None):
+    """BayesNet.loglik (lb.py:103-108) for every row of nets, the way the reference's Python loop evaluates it:
+    torch float32 on the CPU, one vectorised pass per proposal, Normal(yhat, |sigma|).log_prob(y).sum() / n * 50."""
+    import torch
+    import torch.distributions as dist
+    if threads:
+        torch.set_num_threads(threads)
+    xt = torch.as_tensor(np.asarray(x, dtype=np.float32))
+    yt = torch.as_tensor(np.asarray(y, dtype=np.float32))
+    out = np.empty(len(nets), dtype=np.float64)
+    with torch.no_grad():
+        for i, (b0, b1, sg) in enumerate(np.asarray(nets, dtype=np.float32)):
+            yhat = torch.tensor([b0]) + torch.tensor([b1]) * xt
+            logprob = dist.Normal(yhat, torch.tensor([sg]).abs()).log_prob(yt)
+            out[i] = (logprob.sum() / yt.shape[0] * 50).item()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# proposal kernel and acceptance rules (binary64, log domain; loops follow the reference)
+def log_kernel(a, b, ks=1.0):
+    """sum over parameters of log N(a_j; b_j, ks) — log_trans_prob lb.py:111-116 (ks = 1 there), 500_MP.cu:26-28."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sum(-0.5 * math.log(2 * math.pi) - math.log(ks) - 0.5 * ((a - b) / ks) ** 2))
+
+
+def mp_logweights(lt, props, ks=1.0, use_kernel=True):
+    P = len(lt)
+    A = np.empty(P)
+    for j in range(P):                      # lb.py:144-150
+        temp = 0.0
+        for k in range(P):
+            if j != k and use_kernel:
+                temp += log_kernel(props[j], props[k], ks)
+        A[j] = temp + lt[j]
+    return A
+
+
+def _psp_partner(node, c):
+    """The `judg` loop of lb.py:218-238: reduce node modulo 2^(c+1), partner differs in bit c."""
+    judg = node
+    j = 2 ** (c + 1)
+    half_j = j // 2
+    deep = int(math.log2(judg)) if judg > 0 else 0
+    while judg > j - 1:
+        if judg >= 2 ** deep:
+            judg -= 2 ** deep
+        deep -= 1
+    return (judg, judg + half_j) if judg < half_j else (judg, judg - half_j)
+
+
+def psp_logweights(lt, props, depth, ks=1.0, use_kernel=True):
+    P = 2 ** depth
+    A = np.zeros(P)
+    for a in range(P):
+        for c in range(depth):
+            m, q = _psp_partner(a, c)
+            lw_new = lt[m] + (log_kernel(props[m], props[q], ks) if use_kernel else 0.0)
+            lw_old = lt[q] + (log_kernel(props[q], props[m], ks) if use_kernel else 0.0)
+            # log(w_new/(w_new+w_old)), lb.py:240, evaluated stably
+            A[a] += -np.logaddexp(0.0, lw_old - lw_new)
+    return A
+
+
+def pmp_logweights(lt, props, b, depth, ks=1.0, use_kernel=True, quirk_level_mod=False):
+    P = b ** depth
+    A = np.zeros(P)                          # log of lb.py:308's ones
+    for i in range(depth):                   # lb.py:315-330
+        temp = b ** i
+        for h in range(temp):
+            v = np.empty(b)
+            for j in range(b):
+                v[j] = lt[h + j * temp]
+                for k in range(b):
+                    if j != k and use_kernel:
+                        v[j] += log_kernel(props[h + j * temp], props[h + k * temp], ks)
+            mx = np.max(v)
+            lse = mx + math.log(np.sum(np.exp(v - mx))) if np.isfinite(mx) else -np.inf
+            for j in range(b):
+                A[h + j * temp] += (v[j] - lse) if np.isfinite(mx) else -np.inf
+        if i < depth - 1:
+            mod = b * (i + 1) if quirk_level_mod else b ** (i + 1)
+            for l in range(b ** (i + 2) - b ** (i + 1)):
+                A[l + b ** (i + 1)] = A[(l + b ** (i + 1)) % mod]
+    return A
+
+
+def table_logweights(lt, props, b, depth, ks=1.0, quirk_const=False):
+    """lt + sum_d sum_{k != m in group} log K(m,k), m = p mod b^(d+1)  (500_PMP.cu:23-30, conv_pmp.cu:22-33)."""
+    P = b ** depth
+    dim = np.asarray(props).shape[1]
+    A = np.empty(P)
+    for p in range(P):
+        v = lt[p]
+        for d in range(depth):
+            s = b ** d
+            m = p % (s * b)
+            h = m % s
+            for k in range(b):
+                o = h + k * s
+                if o != m:
+                    v += dim * (-0.5 * math.log(2 * math.pi)) if quirk_const else log_kernel(props[m], props[o], ks)
+        A[p] = v
+    return A
+
+
+def standardize(A):
+    """(A - mean)/std with the unbiased std of torch.std (PMP_FC.py:138-140)."""
+    A = np.asarray(A, dtype=np.float64)
+    return (A - A.mean()) / A.std(ddof=1)
+
+
+def weights_from_log(A):
+    A = np.asarray(A, dtype=np.float64)
+    w = np.exp(A - np.max(A))
+    return np.where(np.isnan(w), 0.0, w)
+
+
+def draw_numpy(w, u):
+    """pandas DataFrame.sample(weights=) → np.random.RandomState.choice(p=): verified against both in tests."""
+    p = np.asarray(w, dtype=np.float64)
+    p = p / p.sum()
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    return np.minimum(cdf.searchsorted(np.asarray(u), side="right"), len(p) - 1).astype(np.int32)
+
+
+def draw_libstdcxx(w, u):
+    """std::discrete_distribution (libstdc++ bits/random.tcc): normalise, partial_sum, last = 1, lower_bound."""
+    p = np.asarray(w, dtype=np.float64)
+    p = p / np.sum(p)
+    cp = np.cumsum(p)
+    cp[-1] = 1.0
+    return np.minimum(cp.searchsorted(np.asarray(u), side="left"), len(p) - 1).astype(np.int32)
+
+
+def blocked_cdf(w):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = np.empty_like(w)
+    lib().oracle_blocked_cdf(_dptr(w), len(w), _dptr(out))
+    return out
+
+
+def draw_blocked(w, u, side="right"):
+    cdf = blocked_cdf(w)
+    return np.minimum(cdf.searchsorted(np.asarray(u), side=side), len(w) - 1).astype(np.int32)
+
+
+def pick_index(u_pick, P):
+    """np.random.choice(arange(P), 1) (lb.py:162) driven by one injected uniform."""
+    return min(P - 1, int(u_pick * P))
+
+
+# analytic log-targets ------------------------------------------------------------------------------------------
+def log_normal1d(x, mu, sigma):          # error.py:11-14 (log of)
+    return -0.5 * ((x - mu) / sigma) ** 2 - math.log(sigma) - 0.5 * math.log(2 * math.pi)
+
+
+def log_banana(x):                       # banana_data.ipynb cell 2 L1-5 (log of)
+    x1, x2 = float(x[0]), float(x[1])
+    return -(x1 ** 2) / 2 - ((x2 - 2 * (x1 ** 2 - 5)) ** 2) / 2
+
+
+def log_stdnormal(x):                    # com_dim.py:13-15 with mu=0, cov=I (log of)
+    x = np.asarray(x, dtype=np.float64)
+    return float(-0.5 * np.sum(x * x) - 0.5 * len(x) * math.log(2 * math.pi))

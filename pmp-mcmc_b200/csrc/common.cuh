@@ -1,0 +1,110 @@
+// common.cuh — context layout and small helpers shared by the translation units of libpmp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pmp_b200.h"
+
+namespace pmp {
+
+void set_error(const char* fmt, ...);
+
+#define PMP_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            pmp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PMP_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define PMP_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            pmp::set_error(__VA_ARGS__);  \
+            return PMP_ERR_ARG;           \
+        }                                 \
+    } while (0)
+
+// Fixed-point format of the per-node sums of squared standardised residuals: the sweep converts the float32
+// partial of every CHUNK consecutive data points to an integer multiple of 2^-FX_SHIFT and from there on
+// everything is integer addition — exact and associative, so the per-node sum is bit-identical for any
+// block order, any grid size and any number of GPUs (shards aligned to CHUNK).
+constexpr int CHUNK = 64;
+constexpr int FX_SHIFT = 20;
+constexpr int MAX_NODES = 8192;      // accept kernel keeps two double arrays of P entries in shared memory
+constexpr int KDIM_MAX = 64;         // in-kernel closed-form MP kernel term supports dim <= KDIM_MAX
+
+struct DeviceCounters {
+    unsigned long long iteration;   // Philox iteration counter, advanced by the accept kernel
+    long long trace_rows;           // rows recorded in the trace ring
+    int flags;                      // bit0: fixed-point saturation seen
+    int last_next;                  // accepted node of the last accept
+};
+
+struct TraceBuffers {
+    long long capacity = 0;
+    uint32_t what = 0;
+    float* state = nullptr;
+    int32_t* next = nullptr;
+    int32_t* draws = nullptr;
+    float* samples = nullptr;
+    double* logw = nullptr;
+};
+
+}  // namespace pmp
+
+struct pmp_ctx {
+    int device = 0, world = 1, rank = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    void* nccl_comm = nullptr;
+
+    bool configured = false;
+    pmp_config cfg{};
+    int P = 0;
+
+    // linear-Gaussian data shard
+    float* d_x = nullptr; float* d_y = nullptr;
+    long long n_local = 0, n_offset = 0, n_global = 0;
+
+    // chain
+    uint64_t seed = 0;
+    float* d_state = nullptr;          // [dim]
+    float* d_props = nullptr;          // [P, dim]
+    unsigned long long* d_acc = nullptr;  // [P] fixed-point partial sums (linear-Gaussian)
+    double* d_lt = nullptr;            // [P] log-targets
+    double* d_logw = nullptr;          // [P] log-weights of the last accept
+    int32_t* d_draws = nullptr;        // [P]
+    double* d_uniforms = nullptr;      // [P+1] injected uniforms
+    pmp::DeviceCounters* d_cnt = nullptr;
+    bool lt_valid = false;             // d_lt holds the log-targets of the current proposals
+    bool acc_pending = false;          // d_acc holds an un-finalised sweep
+
+    pmp::TraceBuffers trace;
+
+    // graph cache for pmp_run
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_iters = 0;
+
+    // misc
+    void* d_flush = nullptr; size_t flush_bytes = 0;
+    long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+
+    // batched analytic chains
+    long long n_chains = 0;
+    float* d_chain_states = nullptr;   // [dim, n_chains] (chain fastest)
+    float* d_chain_samples = nullptr;  // [iters, P, dim, n_chains]
+    long long chain_samples_cap = 0;   // in floats
+    long long chain_iters_recorded = 0;
+    unsigned long long chain_iteration = 0;
+
+    // FC model
+    void* fc = nullptr;
+};

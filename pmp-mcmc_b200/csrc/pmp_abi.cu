@@ -1,0 +1,597 @@
+// pmp_abi.cu — the C-ABI of include/pmp_b200.h: context, buffers, kernel launches, device-resident chain loop.
+// No torch types, no CPU fallback: every compute entry point launches sm_100a kernels on the ctx stream.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "accept.cuh"
+#include "common.cuh"
+#include "sweep_linear.cuh"
+
+namespace pmp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+// ---- NCCL, resolved at run time so that libpmp_b200.so has no link-time dependency (and shares torch's libnccl
+// when torch is already loaded in the process).
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.handle) return PMP_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error("NCCL not found: %s", dlerror()); return PMP_ERR_NCCL; }
+    g_nccl.GetUniqueId = (decltype(&ncclGetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(&ncclCommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(&ncclCommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(&ncclAllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(&ncclGetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+        set_error("NCCL symbols missing"); return PMP_ERR_NCCL;
+    }
+    g_nccl.handle = h;
+    return PMP_OK;
+}
+#define PMP_NCCL(expr)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t _r = (expr);                                                                        \
+        if (_r != ncclSuccess) {                                                                         \
+            pmp::set_error("%s failed: %s", #expr, pmp::g_nccl.GetErrorString ? pmp::g_nccl.GetErrorString(_r) : "?"); \
+            return PMP_ERR_NCCL;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+static long long total_chunks_global(const pmp_ctx* c) { return (c->n_global + CHUNK - 1) / CHUNK + c->world; }
+static double sat_limit(const pmp_ctx* c) { return 4611686018427387904.0 / (double)(total_chunks_global(c) > 0 ? total_chunks_global(c) : 1); }
+
+template <typename T> static int dev_alloc(T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return PMP_OK;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e)); return PMP_ERR_ALLOC; }
+    return PMP_OK;
+}
+
+static void drop_graph(pmp_ctx* c) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_iters = 0; }
+}
+
+// ---- launches ------------------------------------------------------------------------------------------------
+static int launch_propose(pmp_ctx* c) {
+    ProposeArgs a{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha};
+    long long total = (long long)c->P * c->cfg.dim;
+    long long blocks = (total + 255) / 256;
+    long long cap = (long long)c->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    propose_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+static int launch_sweep_linear(pmp_ctx* c) {
+    PMP_REQUIRE(c->d_x && c->n_local >= 0, "linear-Gaussian data not set (pmp_set_data_linear)");
+    constexpr int R = 4;
+    int need = (c->P + R - 1) / R;
+    int TP = 1; while (TP < need && TP < SWEEP_THREADS) TP <<= 1;
+    int TD = SWEEP_THREADS / TP;
+    long long nchunks = (c->n_local + CHUNK - 1) / CHUNK;
+    if (nchunks == 0) return PMP_OK;
+    int gy = (c->P + TP * R - 1) / (TP * R);
+    int per_sm = env_int("PMP_SWEEP_BLOCKS_PER_SM", 4);
+    long long gx = ((long long)c->sm_count * per_sm + gy - 1) / gy;
+    long long want = (nchunks + TD - 1) / TD;
+    if (gx > want) gx = want;
+    if (gx < 1) gx = 1;
+    SweepArgs a{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, TP, TD, sat_limit(c)};
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (env_int("PMP_SWEEP_SCALAR", 0)) sweep_linear_kernel<R, false><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    else sweep_linear_kernel<R, true><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+static int allreduce_acc(pmp_ctx* c) {
+    if (c->world <= 1) return PMP_OK;
+    PMP_NCCL(g_nccl.AllReduce(c->d_acc, c->d_acc, (size_t)c->P, ncclUint64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+    return PMP_OK;
+}
+
+static int launch_accept(pmp_ctx* c, int from_acc, int only_finalize, int advance, const double* d_uniforms) {
+    AcceptArgs a{};
+    a.cfg = c->cfg; a.P = c->P; a.n_global = c->n_global; a.state = c->d_state; a.props = c->d_props; a.acc = c->d_acc;
+    a.lt = c->d_lt; a.logw = c->d_logw; a.draws = c->d_draws; a.uniforms = d_uniforms; a.cnt = c->d_cnt; a.seed = c->seed;
+    a.sat_limit = sat_limit(c); a.from_acc = from_acc; a.only_finalize = only_finalize; a.advance = advance; a.trace = c->trace;
+    size_t smem = (size_t)c->P * 2 * sizeof(double);
+    accept_kernel<<<1, ACCEPT_THREADS, smem, c->stream>>>(a);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// one full iteration on the stream: propose → sweep → [all-reduce] → accept
+static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sweep_end) {
+    int rc;
+    if ((rc = launch_propose(c))) return rc;
+    if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS) {
+        if (sweep_begin) PMP_CUDA(cudaEventRecord(sweep_begin, c->stream));
+        if ((rc = launch_sweep_linear(c))) return rc;
+        if (sweep_end) PMP_CUDA(cudaEventRecord(sweep_end, c->stream));
+        if ((rc = allreduce_acc(c))) return rc;
+        return launch_accept(c, 1, 0, 1, nullptr);
+    }
+    if (c->cfg.target == PMP_TARGET_FC || c->cfg.target == PMP_TARGET_EXTERNAL) {
+        set_error("pmp_run: target %d needs host-driven log-targets (use pmp_propose / pmp_write_logtarget / pmp_accept)", c->cfg.target);
+        return PMP_ERR_UNSUPPORTED;
+    }
+    return launch_accept(c, 0, 0, 1, nullptr);
+}
+
+}  // namespace pmp
+
+using namespace pmp;
+
+extern "C" {
+
+const char* pmp_last_error(void) { return g_err; }
+int pmp_abi_version(void) { return PMP_B200_ABI_VERSION; }
+
+int pmp_nccl_unique_id(void* out128) {
+    PMP_REQUIRE(out128, "out128 is NULL");
+    int rc = load_nccl(); if (rc) return rc;
+    ncclUniqueId id;
+    PMP_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return PMP_OK;
+}
+
+int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* nccl_unique_id) {
+    PMP_REQUIRE(out, "out is NULL");
+    PMP_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad world_size/rank %d/%d", world_size, rank);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no usable CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return PMP_ERR_CUDA;
+    }
+    PMP_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    PMP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PMP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; libpmp_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return PMP_ERR_UNSUPPORTED;
+    }
+    pmp_ctx* c = new pmp_ctx();
+    c->device = device; c->world = world_size; c->rank = rank; c->sm_count = prop.multiProcessorCount;
+    PMP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PMP_CUDA(cudaEventCreate(&c->ev0)); PMP_CUDA(cudaEventCreate(&c->ev1));
+    PMP_CUDA(cudaMalloc((void**)&c->d_cnt, sizeof(DeviceCounters)));
+    PMP_CUDA(cudaMemset(c->d_cnt, 0, sizeof(DeviceCounters)));
+    PMP_CUDA(cudaFuncSetAttribute(accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_NODES * 2 * (int)sizeof(double)));
+    if (world_size > 1) {
+        PMP_REQUIRE(nccl_unique_id, "world_size > 1 needs an NCCL unique id");
+        int rc = load_nccl(); if (rc) { delete c; return rc; }
+        ncclUniqueId id; memcpy(&id, nccl_unique_id, sizeof(id));
+        ncclComm_t comm;
+        PMP_NCCL(g_nccl.CommInitRank(&comm, world_size, id, rank));
+        c->nccl_comm = comm;
+    }
+    *out = c;
+    return PMP_OK;
+}
+
+int pmp_fc_destroy(pmp_ctx* ctx);   // fc_sweep.cu
+
+int pmp_destroy(pmp_ctx* c) {
+    if (!c) return PMP_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    drop_graph(c);
+    pmp_fc_destroy(c);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
+    void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush,
+                    c->d_chain_states, c->d_chain_samples};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return PMP_OK;
+}
+
+int pmp_device_info(pmp_ctx* c, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
+    PMP_REQUIRE(c, "ctx is NULL");
+    cudaDeviceProp prop;
+    PMP_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_len > 0) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return PMP_OK;
+}
+
+int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
+    PMP_REQUIRE(c && cfg, "NULL argument");
+    PMP_CUDA(cudaSetDevice(c->device));
+    long long P;
+    if (cfg->tree == PMP_TREE_FLAT) P = cfg->b;
+    else if (cfg->tree == PMP_TREE_BINARY) P = 1ll << cfg->depth;
+    else if (cfg->tree == PMP_TREE_BARY) P = ipow(cfg->b, cfg->depth);
+    else { set_error("unknown tree kind %d", cfg->tree); return PMP_ERR_ARG; }
+    PMP_REQUIRE(cfg->tree == PMP_TREE_FLAT || (cfg->depth >= 1 && cfg->depth <= 13), "depth %d out of range", cfg->depth);
+    PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY || cfg->b >= 1, "b=%d must be >= 1", cfg->b);
+    PMP_REQUIRE(P >= 1 && P <= MAX_NODES, "P=%lld nodes out of range [1,%d]", P, MAX_NODES);
+    PMP_REQUIRE(cfg->dim >= 1, "dim must be >= 1");
+    PMP_REQUIRE(cfg->target >= 0 && cfg->target <= PMP_TARGET_EXTERNAL, "unknown target %d", cfg->target);
+    PMP_REQUIRE(cfg->algo >= 0 && cfg->algo <= PMP_ALGO_TABLE, "unknown algo %d", cfg->algo);
+    PMP_REQUIRE(cfg->draw >= 0 && cfg->draw <= PMP_DRAW_SINGLE, "unknown draw rule %d", cfg->draw);
+    if (cfg->target == PMP_TARGET_LINEAR_GAUSS) PMP_REQUIRE(cfg->dim == 3, "linear-Gaussian target has dim 3 (b0,b1,sigma), got %d", cfg->dim);
+    if (cfg->target == PMP_TARGET_NORMAL1D) PMP_REQUIRE(cfg->dim == 1, "NORMAL1D has dim 1");
+    if (cfg->target == PMP_TARGET_BANANA) PMP_REQUIRE(cfg->dim == 2, "BANANA has dim 2");
+    if (cfg->algo == PMP_ALGO_MH || cfg->algo == PMP_ALGO_BARKER) PMP_REQUIRE(P == 2, "MH/BARKER need P == 2 (FLAT, b=2), got %lld", P);
+    if (cfg->algo == PMP_ALGO_PSP) PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY, "PSP needs the BINARY tree");
+    if (cfg->algo == PMP_ALGO_PMP) PMP_REQUIRE(cfg->tree == PMP_TREE_BARY || cfg->tree == PMP_TREE_BINARY, "PMP needs a BARY/BINARY tree");
+    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC)
+        PMP_REQUIRE(cfg->dim <= KDIM_MAX, "in-kernel MP kernel term supports dim <= %d", KDIM_MAX);
+    PMP_REQUIRE(cfg->scale != 0.f && cfg->kernel_sigma > 0.f, "scale must be non-zero and kernel_sigma > 0");
+
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    drop_graph(c);
+    bool realloc_state = !c->configured || c->cfg.dim != cfg->dim;
+    c->cfg = *cfg; c->P = (int)P;
+    int rc;
+    if (realloc_state) {
+        if ((rc = dev_alloc(&c->d_state, (size_t)cfg->dim))) return rc;
+        PMP_CUDA(cudaMemset(c->d_state, 0, cfg->dim * sizeof(float)));
+    }
+    if ((rc = dev_alloc(&c->d_props, (size_t)P * cfg->dim))) return rc;
+    if ((rc = dev_alloc(&c->d_acc, (size_t)P))) return rc;
+    if ((rc = dev_alloc(&c->d_lt, (size_t)P))) return rc;
+    if ((rc = dev_alloc(&c->d_logw, (size_t)P))) return rc;
+    if ((rc = dev_alloc(&c->d_draws, (size_t)P))) return rc;
+    if ((rc = dev_alloc(&c->d_uniforms, (size_t)P + 1))) return rc;
+    PMP_CUDA(cudaMemset(c->d_acc, 0, P * sizeof(unsigned long long)));
+    PMP_CUDA(cudaMemset(c->d_props, 0, (size_t)P * cfg->dim * sizeof(float)));
+    PMP_CUDA(cudaMemset(c->d_lt, 0, P * sizeof(double)));
+    PMP_CUDA(cudaMemset(c->d_logw, 0, P * sizeof(double)));
+    c->lt_valid = false; c->acc_pending = false;
+    c->configured = true;
+    // trace buffers depend on P and dim
+    c->trace = TraceBuffers{};
+    return PMP_OK;
+}
+
+int pmp_num_nodes(pmp_ctx* c) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    return c->P;
+}
+
+int pmp_set_data_linear(pmp_ctx* c, const float* x, const float* y, int64_t n_local, int64_t n_offset, int64_t n_global) {
+    PMP_REQUIRE(c, "ctx is NULL");
+    PMP_REQUIRE(n_local >= 0 && n_global >= n_local && n_offset >= 0 && n_offset + n_local <= n_global, "bad shard [%lld,+%lld) of %lld",
+                (long long)n_offset, (long long)n_local, (long long)n_global);
+    PMP_REQUIRE(n_local == 0 || (x && y), "x/y NULL");
+    PMP_CUDA(cudaSetDevice(c->device));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    drop_graph(c);
+    int rc;
+    size_t padded = ((size_t)n_local + 3) / 4 * 4 + 4;
+    if ((rc = dev_alloc(&c->d_x, padded))) return rc;
+    if ((rc = dev_alloc(&c->d_y, padded))) return rc;
+    PMP_CUDA(cudaMemsetAsync(c->d_x, 0, padded * sizeof(float), c->stream));
+    PMP_CUDA(cudaMemsetAsync(c->d_y, 0, padded * sizeof(float), c->stream));
+    if (n_local) {
+        PMP_CUDA(cudaMemcpyAsync(c->d_x, x, n_local * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        PMP_CUDA(cudaMemcpyAsync(c->d_y, y, n_local * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_local = n_local; c->n_offset = n_offset; c->n_global = n_global;
+    return PMP_OK;
+}
+
+int pmp_set_state(pmp_ctx* c, const float* theta, int dim) {
+    PMP_REQUIRE(c && c->configured && theta, "ctx not configured or theta NULL");
+    PMP_REQUIRE(dim == c->cfg.dim, "dim %d != configured %d", dim, c->cfg.dim);
+    PMP_CUDA(cudaMemcpyAsync(c->d_state, theta, dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_get_state(pmp_ctx* c, float* theta, int dim) {
+    PMP_REQUIRE(c && c->configured && theta, "ctx not configured or theta NULL");
+    PMP_REQUIRE(dim == c->cfg.dim, "dim %d != configured %d", dim, c->cfg.dim);
+    PMP_CUDA(cudaMemcpyAsync(theta, c->d_state, dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_seed(pmp_ctx* c, uint64_t seed, uint64_t iteration) {
+    PMP_REQUIRE(c, "ctx is NULL");
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    if (seed != c->seed) drop_graph(c);   // the key is a baked kernel argument
+    c->seed = seed;
+    unsigned long long it = iteration;
+    PMP_CUDA(cudaMemcpyAsync(&c->d_cnt->iteration, &it, sizeof(it), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_get_iteration(pmp_ctx* c, uint64_t* iteration) {
+    PMP_REQUIRE(c && iteration, "NULL argument");
+    unsigned long long it;
+    PMP_CUDA(cudaMemcpyAsync(&it, &c->d_cnt->iteration, sizeof(it), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    *iteration = it;
+    return PMP_OK;
+}
+
+int pmp_propose(pmp_ctx* c) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_CUDA(cudaSetDevice(c->device));
+    c->lt_valid = false;
+    return launch_propose(c);
+}
+
+int pmp_read_proposals(pmp_ctx* c, float* out, int64_t count) {
+    PMP_REQUIRE(c && c->configured && out, "ctx not configured or out NULL");
+    PMP_REQUIRE(count == (int64_t)c->P * c->cfg.dim, "count %lld != P*dim = %lld", (long long)count, (long long)c->P * c->cfg.dim);
+    PMP_CUDA(cudaMemcpyAsync(out, c->d_props, count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_write_proposals(pmp_ctx* c, const float* in, int64_t count) {
+    PMP_REQUIRE(c && c->configured && in, "ctx not configured or in NULL");
+    PMP_REQUIRE(count == (int64_t)c->P * c->cfg.dim, "count %lld != P*dim = %lld", (long long)count, (long long)c->P * c->cfg.dim);
+    PMP_CUDA(cudaMemcpyAsync(c->d_props, in, count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    c->lt_valid = false;
+    return PMP_OK;
+}
+
+int pmp_fc_loglik(pmp_ctx* c);   // fc_sweep.cu: fills d_lt for PMP_TARGET_FC
+
+int pmp_loglik(pmp_ctx* c, double* out_host) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS) {
+        if ((rc = launch_sweep_linear(c))) return rc;
+        if ((rc = allreduce_acc(c))) return rc;
+        if ((rc = launch_accept(c, 1, 1, 0, nullptr))) return rc;
+    } else if (c->cfg.target == PMP_TARGET_FC) {
+        if ((rc = pmp_fc_loglik(c))) return rc;
+    } else if (c->cfg.target == PMP_TARGET_EXTERNAL) {
+        PMP_REQUIRE(c->lt_valid, "EXTERNAL target: call pmp_write_logtarget first");
+    } else {
+        if ((rc = launch_accept(c, 0, 1, 0, nullptr))) return rc;
+    }
+    c->lt_valid = true;
+    if (out_host) {
+        PMP_CUDA(cudaMemcpyAsync(out_host, c->d_lt, c->P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PMP_OK;
+}
+
+int pmp_write_logtarget(pmp_ctx* c, const double* in, int64_t count) {
+    PMP_REQUIRE(c && c->configured && in, "ctx not configured or in NULL");
+    PMP_REQUIRE(count == c->P, "count %lld != P = %d", (long long)count, c->P);
+    PMP_CUDA(cudaMemcpyAsync(c->d_lt, in, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    c->lt_valid = true;
+    return PMP_OK;
+}
+
+static int uniforms_needed(const pmp_ctx* c) {
+    if (c->cfg.algo == PMP_ALGO_MH || c->cfg.algo == PMP_ALGO_BARKER || c->cfg.draw == PMP_DRAW_SINGLE) return 1;
+    return c->cfg.draw == PMP_DRAW_PYTHON ? c->P + 1 : c->P;
+}
+
+int pmp_accept(pmp_ctx* c, const double* uniforms, int64_t n_uniforms, int32_t* idx_out, int32_t* next_out) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_REQUIRE(c->lt_valid, "pmp_accept before pmp_loglik / pmp_write_logtarget");
+    PMP_CUDA(cudaSetDevice(c->device));
+    const double* d_u = nullptr;
+    if (uniforms) {
+        PMP_REQUIRE(n_uniforms == uniforms_needed(c), "need %d uniforms for this draw rule, got %lld", uniforms_needed(c), (long long)n_uniforms);
+        PMP_CUDA(cudaMemcpyAsync(c->d_uniforms, uniforms, n_uniforms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        d_u = c->d_uniforms;
+    }
+    int rc = launch_accept(c, 0, 0, 1, d_u);
+    if (rc) return rc;
+    c->lt_valid = false;
+    if (idx_out || next_out || uniforms) {
+        int nd = (c->cfg.algo == PMP_ALGO_MH || c->cfg.algo == PMP_ALGO_BARKER || c->cfg.draw == PMP_DRAW_SINGLE) ? 1 : c->P;
+        if (idx_out) PMP_CUDA(cudaMemcpyAsync(idx_out, c->d_draws, nd * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (next_out) PMP_CUDA(cudaMemcpyAsync(next_out, &c->d_cnt->last_next, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PMP_OK;
+}
+
+int pmp_read_logweights(pmp_ctx* c, double* out, int64_t count) {
+    PMP_REQUIRE(c && c->configured && out, "ctx not configured or out NULL");
+    PMP_REQUIRE(count == c->P, "count %lld != P = %d", (long long)count, c->P);
+    PMP_CUDA(cudaMemcpyAsync(out, c->d_logw, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_trace_config(pmp_ctx* c, int64_t max_iters, uint32_t what) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_REQUIRE(max_iters >= 0, "max_iters < 0");
+    PMP_CUDA(cudaSetDevice(c->device));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    drop_graph(c);
+    int rc;
+    size_t n = (size_t)max_iters, P = c->P, dim = c->cfg.dim;
+    if ((rc = dev_alloc(&c->trace.state, (what & PMP_TRACE_STATE) ? n * dim : 0))) return rc;
+    if ((rc = dev_alloc(&c->trace.next, (what & PMP_TRACE_NEXT) ? n : 0))) return rc;
+    if ((rc = dev_alloc(&c->trace.draws, (what & PMP_TRACE_DRAWS) ? n * P : 0))) return rc;
+    if ((rc = dev_alloc(&c->trace.samples, (what & PMP_TRACE_SAMPLES) ? n * P * dim : 0))) return rc;
+    if ((rc = dev_alloc(&c->trace.logw, (what & PMP_TRACE_LOGW) ? n * P : 0))) return rc;
+    c->trace.capacity = max_iters; c->trace.what = what;
+    long long zero = 0;
+    PMP_CUDA(cudaMemcpyAsync(&c->d_cnt->trace_rows, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_trace_reset(pmp_ctx* c) {
+    PMP_REQUIRE(c, "ctx is NULL");
+    long long zero = 0;
+    PMP_CUDA(cudaMemcpyAsync(&c->d_cnt->trace_rows, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_read_trace(pmp_ctx* c, int64_t max_iters, float* state, int32_t* next, int32_t* draws, float* samples, double* logw,
+                   int64_t* n_recorded) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    long long rows = 0;
+    PMP_CUDA(cudaMemcpyAsync(&rows, &c->d_cnt->trace_rows, sizeof(rows), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    if (rows > max_iters) rows = max_iters;
+    size_t n = (size_t)rows, P = c->P, dim = c->cfg.dim;
+    if (state) { PMP_REQUIRE(c->trace.state, "STATE not traced"); PMP_CUDA(cudaMemcpyAsync(state, c->trace.state, n * dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); }
+    if (next) { PMP_REQUIRE(c->trace.next, "NEXT not traced"); PMP_CUDA(cudaMemcpyAsync(next, c->trace.next, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream)); }
+    if (draws) { PMP_REQUIRE(c->trace.draws, "DRAWS not traced"); PMP_CUDA(cudaMemcpyAsync(draws, c->trace.draws, n * P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream)); }
+    if (samples) { PMP_REQUIRE(c->trace.samples, "SAMPLES not traced"); PMP_CUDA(cudaMemcpyAsync(samples, c->trace.samples, n * P * dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); }
+    if (logw) { PMP_REQUIRE(c->trace.logw, "LOGW not traced"); PMP_CUDA(cudaMemcpyAsync(logw, c->trace.logw, n * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream)); }
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_recorded) *n_recorded = rows;
+    return PMP_OK;
+}
+
+// The chain loop.  A CUDA graph of GRAPH_ITERS iterations is captured once per configuration and replayed, so the
+// host issues one launch per GRAPH_ITERS iterations; the iteration counter, the state and the trace cursor live on the
+// device, so replay needs no parameter update.
+static int run_impl(pmp_ctx* c, int64_t iters) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_REQUIRE(iters >= 0, "iters < 0");
+    PMP_CUDA(cudaSetDevice(c->device));
+    const int GI = env_int("PMP_GRAPH_ITERS", 32);
+    int rc;
+    int64_t done = 0;
+    if (GI > 1 && iters >= GI) {
+        if (!c->graph_exec || c->graph_iters != GI) {
+            drop_graph(c);
+            cudaGraph_t graph;
+            PMP_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            rc = PMP_OK;
+            for (int i = 0; i < GI && rc == PMP_OK; ++i) rc = enqueue_iteration(c, nullptr, nullptr);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+            PMP_CUDA(e);
+            PMP_CUDA(cudaGraphInstantiate(&c->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            c->graph_iters = GI;
+            c->launches -= (long long)GI * (c->cfg.target == PMP_TARGET_LINEAR_GAUSS ? 3 : 2);   // capture enqueues are not launches
+        }
+        const long long per_iter = (c->cfg.target == PMP_TARGET_LINEAR_GAUSS ? 3 : 2);
+        for (; done + GI <= iters; done += GI) { PMP_CUDA(cudaGraphLaunch(c->graph_exec, c->stream)); c->launches += per_iter * GI; }
+    }
+    for (; done < iters; ++done) if ((rc = enqueue_iteration(c, nullptr, nullptr))) return rc;
+    c->lt_valid = false;
+    return PMP_OK;
+}
+
+int pmp_run(pmp_ctx* c, int64_t iters, int sync) {
+    int rc = run_impl(c, iters);
+    if (rc) return rc;
+    if (sync) PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_sync(pmp_ctx* c) {
+    PMP_REQUIRE(c, "ctx is NULL");
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_run_timed(pmp_ctx* c, int64_t iters, float* total_ms, float* sweep_ms) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_CUDA(cudaSetDevice(c->device));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    int rc;
+    if (!sweep_ms) {
+        PMP_CUDA(cudaEventRecord(c->ev0, c->stream));
+        if ((rc = run_impl(c, iters))) return rc;
+        PMP_CUDA(cudaEventRecord(c->ev1, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        // per-iteration event pairs around the sweep kernel (plain launches, no graph)
+        PMP_REQUIRE(iters <= 4096, "sweep timing mode supports <= 4096 iterations per call");
+        while ((int64_t)c->ev_pool.size() < 2 * iters) { cudaEvent_t ev; PMP_CUDA(cudaEventCreate(&ev)); c->ev_pool.push_back(ev); }
+        PMP_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int64_t i = 0; i < iters; ++i) if ((rc = enqueue_iteration(c, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]))) return rc;
+        PMP_CUDA(cudaEventRecord(c->ev1, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+        double acc = 0.0;
+        if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS)
+            for (int64_t i = 0; i < iters; ++i) { float ms = 0.f; PMP_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1])); acc += ms; }
+        *sweep_ms = (float)acc;
+        c->lt_valid = false;
+    }
+    if (total_ms) PMP_CUDA(cudaEventElapsedTime(total_ms, c->ev0, c->ev1));
+    return PMP_OK;
+}
+
+int pmp_launch_count(pmp_ctx* c, int64_t* launches) {
+    PMP_REQUIRE(c && launches, "NULL argument");
+    *launches = c->launches;
+    return PMP_OK;
+}
+
+int pmp_fp32_peak(pmp_ctx* c, int packed, double* tflops) {
+    PMP_REQUIRE(c && tflops, "NULL argument");
+    PMP_CUDA(cudaSetDevice(c->device));
+    float* d_out; PMP_CUDA(cudaMalloc((void**)&d_out, 4));
+    const int iters = 16384, blocks = c->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        PMP_CUDA(cudaEventRecord(c->ev0, c->stream));
+        if (packed) fp32_peak_kernel<true><<<blocks, 256, 0, c->stream>>>(d_out, iters, 1.0f);
+        else fp32_peak_kernel<false><<<blocks, 256, 0, c->stream>>>(d_out, iters, 1.0f);
+        c->launches++;
+        PMP_CUDA(cudaEventRecord(c->ev1, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+        float ms; PMP_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        double flops = (double)blocks * 256.0 * iters * 8.0 * 2.0 * 2.0;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaFree(d_out);
+    *tflops = best;
+    return PMP_OK;
+}
+
+int pmp_l2_flush(pmp_ctx* c) {
+    PMP_REQUIRE(c, "ctx is NULL");
+    PMP_CUDA(cudaSetDevice(c->device));
+    if (!c->d_flush) { c->flush_bytes = 256ull << 20; PMP_CUDA(cudaMalloc(&c->d_flush, c->flush_bytes)); }
+    PMP_CUDA(cudaMemsetAsync(c->d_flush, 0x5a, c->flush_bytes, c->stream));
+    return PMP_OK;
+}
+
+}  // extern "C"
