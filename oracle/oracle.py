@@ -178,6 +178,15 @@ def log_kernel(a, b, ks=1.0):
 
 def mp_logweights(lt, props, ks=1.0, use_kernel=True):
     P = len(lt)
+    if P > 64:                              # same sums as the loop below, one row of pairs at a time (the loop is O(P^2) Python)
+        th = np.asarray(props, dtype=np.float64)
+        A = np.array(lt, dtype=np.float64)
+        if use_kernel:
+            c = th.shape[1] * (-0.5 * math.log(2 * math.pi) - math.log(ks))
+            for j in range(P):
+                d2 = np.sum(((th[j] - th) / ks) ** 2, axis=1)
+                A[j] += (P - 1) * c - 0.5 * (np.sum(d2) - d2[j])
+        return A
     A = np.empty(P)
     for j in range(P):                      # lb.py:144-150
         temp = 0.0
@@ -210,7 +219,8 @@ def psp_logweights(lt, props, depth, ks=1.0, use_kernel=True):
             lw_new = lt[m] + (log_kernel(props[m], props[q], ks) if use_kernel else 0.0)
             lw_old = lt[q] + (log_kernel(props[q], props[m], ks) if use_kernel else 0.0)
             # log(w_new/(w_new+w_old)), lb.py:240, evaluated stably
-            A[a] += -np.logaddexp(0.0, lw_old - lw_new)
+            with np.errstate(invalid="ignore"):
+                A[a] += -np.logaddexp(0.0, lw_old - lw_new)
     return A
 
 
@@ -263,8 +273,12 @@ def standardize(A):
 
 
 def weights_from_log(A):
+    """exp(A - max A) with the maximum taken over the non-NaN entries; NaN log-weights (0/0 in the reference's linear
+    domain, e.g. two dead partner nodes in the Barker tree — pandas would raise there) get weight 0, as on the device."""
     A = np.asarray(A, dtype=np.float64)
-    w = np.exp(A - np.max(A))
+    m = np.nanmax(A) if np.any(~np.isnan(A)) else 0.0
+    with np.errstate(invalid="ignore"):
+        w = np.exp(A - m)
     return np.where(np.isnan(w), 0.0, w)
 
 
@@ -294,8 +308,10 @@ def blocked_cdf(w):
 
 
 def draw_blocked(w, u, side="right"):
+    """The device's draw, association for association: unnormalised blocked cdf compared with u * total."""
     cdf = blocked_cdf(w)
-    return np.minimum(cdf.searchsorted(np.asarray(u), side=side), len(w) - 1).astype(np.int32)
+    thr = np.asarray(u, dtype=np.float64) * cdf[-1]
+    return np.minimum(cdf.searchsorted(thr, side=side), len(w) - 1).astype(np.int32)
 
 
 def pick_index(u_pick, P):

@@ -232,7 +232,7 @@ void oracle_sumsq_fixed_mirror(const float* x, const float* y, int64_t n, const 
 /* ------------------------------------------------------------------------------------------------------------
  * 4. Mirror of the device's blocked inclusive scan (csrc/accept.cuh: block_inclusive_scan) for exact cdf equality. */
 void oracle_blocked_cdf(const double* w, int P, double* cdf) {
-    const int T = 1024;
+    const int T = 1024;   /* ACCEPT_THREADS */
     int ipt = (P + T - 1) / T;
     double* run = (double*)calloc(T, sizeof(double));
     double* incl = (double*)calloc(T, sizeof(double));
@@ -248,7 +248,7 @@ void oracle_blocked_cdf(const double* w, int P, double* cdf) {
             for (int l = o; l < 32; ++l) incl[wp * 32 + l] = tmp[l - o] + tmp[l];
         }
     double wt[32];
-    for (int wp = 0; wp < 32; ++wp) wt[wp] = incl[wp * 32 + 31];
+    for (int wp = 0; wp < 32; ++wp) wt[wp] = wp < T / 32 ? incl[wp * 32 + 31] : 0.0;
     for (int o = 1; o < 32; o <<= 1) {
         double tmp[32]; memcpy(tmp, wt, sizeof(tmp));
         for (int l = o; l < 32; ++l) wt[l] = tmp[l - o] + tmp[l];
@@ -260,7 +260,5 @@ void oracle_blocked_cdf(const double* w, int P, double* cdf) {
         double excl = woff + lex;
         for (int i = 0; i < ipt; ++i) { int k = t * ipt + i; if (k < P) cdf[k] = excl + cdf[k]; }
     }
-    double total = cdf[P - 1];
-    for (int k = 0; k < P; ++k) cdf[k] = cdf[k] / total;
-    free(run); free(incl);
+    free(run); free(incl);   /* unnormalised: the device compares cdf_k with u * cdf[P-1] */
 }

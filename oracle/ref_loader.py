@@ -1,0 +1,86 @@
+"""ref_loader.py — import the REFERENCE's own Python definitions from /root/reference.  TEST INFRASTRUCTURE ONLY.
+
+Works only where the reference tree is mounted (the build container); nothing on the GPU box may call it.  The reference
+scripts run experiments at import time, so only their definition part is exec'd: lb.py lines 1-376,
+error.py 1-190, com_dim.py 1-86; matplotlib (absent here) is stubbed.  Used by oracle/make_golden.py to pin
+oracle/oracle.py and pmp_oracle.c against the real code, and by the CPU test-suite when the tree is present."""
+import os
+import sys
+import types
+
+REF = os.environ.get("PMP_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(REF)
+
+
+def _stub_matplotlib():
+    if "matplotlib" not in sys.modules:
+        m = types.ModuleType("matplotlib")
+        p = types.ModuleType("matplotlib.pyplot")
+        m.pyplot = p
+        sys.modules["matplotlib"] = m
+        sys.modules["matplotlib.pyplot"] = p
+
+
+def _exec_head(relpath, nlines, extra_globals=None):
+    _stub_matplotlib()
+    path = os.path.join(REF, relpath)
+    with open(path, encoding="utf-8-sig") as f:
+        src = "".join(f.readlines()[:nlines])
+    ns = {"__name__": "pmp_reference_" + os.path.basename(relpath).replace(".", "_")}
+    if extra_globals:
+        ns.update(extra_globals)
+    exec(compile(src, path, "exec"), ns)
+    return ns
+
+
+def load_lb():
+    """simple_net/lb.py: BayesNet, BayesNet_o, log_trans_prob, MetropolisOptimizer, GMOptimizer, preMOptimizer, GMpreOptimizerV2."""
+    return _exec_head("simple_net/lb.py", 376)
+
+
+def load_error():
+    """simple_sampling/error/error.py: normal, SP, MP, PSP, PMP."""
+    return _exec_head("simple_sampling/error/error.py", 190)
+
+
+def load_com_dim(sigma=0.5):
+    """complex_nets/correlation/com_dim.py: normal, transition_prob, PMP (reads the module-global `sigma`, set at L102)."""
+    return _exec_head("complex_nets/correlation/com_dim.py", 86, {"sigma": sigma})
+
+
+def load_banana():
+    """banana_distribution from banana_data.ipynb cell 2 lines 1-5."""
+    import json
+    import numpy as np
+    with open(os.path.join(REF, "simple_sampling/error/banana/banana_data.ipynb")) as f:
+        nb = json.load(f)
+    cell = [c for c in nb["cells"] if c["cell_type"] == "code"][2]
+    src = "".join(cell["source"][:5])
+    ns = {"np": np}
+    exec(compile(src, "banana_data.ipynb#cell2", "exec"), ns)
+    return ns["banana_distribution"]
+
+
+def load_fc(kind, X, y, device="cpu"):
+    """complex_nets/Mnist/FC/{MH,MP,PMP}_FC.py: Model, loss and the optimizer class, with the MNIST download replaced by
+    injected globals X [n,28,28] float32, y [n] int64 (BASELINE config 5: synthetic MNIST-shaped data)."""
+    import copy
+    import math
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from torch import nn
+    path = os.path.join(REF, "complex_nets/Mnist/FC/%s_FC.py" % kind)
+    with open(path, encoding="utf-8-sig") as f:
+        lines = f.readlines()
+    ns = {"torch": torch, "F": F, "nn": nn, "copy": copy, "math": math, "np": np, "tqdm": lambda it: it, "device": device,
+          "X": X, "y": y, "x_test": X[:16], "y_test": y[:16], "batch_size": int(X.shape[0]), "N": 7, "alpha": 1e-4}
+    ranges = {"PMP": [(20, 44), (77, 186)], "MP": [(20, 36), (68, 74), (76, 158)], "MH": [(15, 31), (66, 136)]}[kind]
+    src = ""
+    for a, b in ranges:
+        src += "".join(lines[a:b]) + "\n"
+    exec(compile(src, path, "exec"), ns)
+    return ns

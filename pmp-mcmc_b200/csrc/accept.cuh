@@ -15,8 +15,11 @@
 
 namespace pmp {
 
-constexpr int ACCEPT_THREADS = 1024;
+constexpr int ACCEPT_THREADS = 1024;    // one CTA; one node per thread at P = 1024
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PMP_STAMP(buf, slot) do { if ((buf) && threadIdx.x == 0) { (buf)[(slot)] = clock64(); (buf)[(slot) + 16] = pmp::globaltimer_ns(); } } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
 // tree index helpers.  Node ids are the reference's: BINARY node k+2^l is the child of k at level l;
@@ -31,7 +34,7 @@ struct ProposeArgs {
 // One thread per (node, coordinate).  The value is built along the node's ancestor chain in float32 with the
 // reference's two roundings per step: child = fl(parent + fl(alpha * z))  (normal_distribution<float>(0, alpha),
 // torch.normal(0, alpha)).  z for the step that created node `a` is normal number a*dim + j of the iteration.
-__device__ __forceinline__ float proposal_value(const ProposeArgs& a, unsigned long long iter, int node, int j, float v) {
+__device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long long iter, int node, int j, float v) {
     if (a.tree == PMP_TREE_FLAT) {
         if (node > 0) {
             float z = (float)stream_normal(a.seed, iter, STREAM_PROPOSAL, (unsigned long long)node * a.dim + j);
@@ -98,6 +101,8 @@ struct AcceptArgs {
     int from_acc;                    // 1: finalise lt from acc; 0: lt already holds the log-targets
     int only_finalize;               // 1: stop after writing lt (pmp_loglik)
     int advance;                     // 1: update state, iteration and trace
+    double inv_scale;                // 1 / cfg.scale (binary64 reciprocal of the float32 scale)
+    unsigned long long* dbg;         // optional phase stamps (PMP_DEBUG_STAMPS=1): [32..63] accept kernel
     TraceBuffers trace;
 };
 
@@ -158,30 +163,37 @@ __device__ __forceinline__ void block_inclusive_scan(double* w, int P, double* r
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a) {
-    extern __shared__ double sm[];
+// Runs in one CTA of ACCEPT_THREADS threads; `sm` = 2*P doubles of shared memory.  ALGO is a template parameter so that
+// each instantiation carries only its own weight rule: the kernel runs once per iteration on one SM, so its code
+// footprint (instruction-cache misses) and dependent-latency chain are what it costs.
+template <int ALGO>
+__device__ __forceinline__ void accept_device(const AcceptArgs& a, double* sm) {
     double* lt = sm;               // [P]
     double* A = sm + a.P;          // [P] log-weights → weights → cdf
     __shared__ double red[32];
+    __shared__ double sred4[128];
     __shared__ double s1[KDIM_MAX];
-    __shared__ double s_misc[4];
     __shared__ int s_next;
 
     const int P = a.P, dim = a.cfg.dim, tid = threadIdx.x;
+    unsigned long long* dbg = a.dbg ? a.dbg + 32 : nullptr;
+    PMP_STAMP(dbg, 0);
     const pmp_config& cfg = a.cfg;
     const unsigned long long iter = a.cnt->iteration;
     const long long row = a.cnt->trace_rows;
     const double ks = (double)cfg.kernel_sigma;
+    const double log_norm_k = (cfg.kernel_sigma == 1.0f) ? -HALF_LOG_2PI : -HALF_LOG_2PI - log(ks);   // per-coordinate log normaliser of K
+    const double half_inv_ks2 = 0.5 / (ks * ks);
 
     // ---- 1. log-targets ------------------------------------------------------------------------------------
     for (int p = tid; p < P; p += ACCEPT_THREADS) {
         double v;
         if (a.from_acc) {
-            unsigned long long q = a.acc[p];
+            unsigned long long q = __ldcg(a.acc + p);
             a.acc[p] = 0ull;
-            double sg = (double)a.props[(long long)p * 3 + 2];
+            double sg = (double)__ldcg(a.props + (long long)p * 3 + 2);
             double S = (double)(long long)q * (1.0 / (double)(1 << FX_SHIFT));
-            v = (-0.5 * (double)a.n_global * log(6.283185307179586477 * sg * sg) - 0.5 * S) / (double)cfg.scale;
+            v = (-0.5 * (double)a.n_global * log(6.283185307179586477 * sg * sg) - 0.5 * S) * a.inv_scale;
             if ((double)(long long)q >= a.sat_limit || !(v == v)) v = -INFINITY;
         } else if (cfg.target == PMP_TARGET_NORMAL1D || cfg.target == PMP_TARGET_BANANA || cfg.target == PMP_TARGET_STDNORMAL) {
             v = analytic_logtarget(cfg.target, a.props + (long long)p * dim, 1, dim, cfg.target_p0, cfg.target_p1) / (double)cfg.scale;
@@ -192,6 +204,7 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
         a.lt[p] = v;
     }
     __syncthreads();
+    PMP_STAMP(dbg, 1);
     if (a.only_finalize) return;
 
     const bool use_kernel = !(cfg.flags & PMP_FLAG_NO_KERNEL_TERM);
@@ -199,23 +212,46 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
     const int D = (cfg.tree == PMP_TREE_FLAT) ? 1 : cfg.depth;
 
     // ---- 2. log-weights ------------------------------------------------------------------------------------
-    if (cfg.algo == PMP_ALGO_MH || cfg.algo == PMP_ALGO_BARKER) {
+    if constexpr (ALGO == PMP_ALGO_MH) {
         for (int p = tid; p < P; p += ACCEPT_THREADS) A[p] = lt[p];
-    } else if (cfg.algo == PMP_ALGO_MP) {
+    } else if constexpr (ALGO == PMP_ALGO_MP) {
         // sum_{k != j} log K(j,k) in closed form about the current state: sum_k |d_j - d_k|^2 = P|d_j|^2 - 2 d_j.S1 + S2
         if (use_kernel && dim <= KDIM_MAX) {
             double my2 = 0.0;
-            for (int j = 0; j < dim; ++j) {
-                double part = 0.0;
+            if (dim <= 3) {
+                // one pass, one 4-value block reduction (S1 per coordinate, S2)
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
                 for (int p = tid; p < P; p += ACCEPT_THREADS) {
-                    double d = (double)a.props[(long long)p * dim + j] - (double)a.props[j];
-                    part += d; my2 = fma(d, d, my2);
+                    double d0 = (double)__ldcg(a.props + (long long)p * dim) - (double)__ldcg(a.props);
+                    double d1 = dim > 1 ? (double)__ldcg(a.props + (long long)p * dim + 1) - (double)__ldcg(a.props + 1) : 0.0;
+                    double d2 = dim > 2 ? (double)__ldcg(a.props + (long long)p * dim + 2) - (double)__ldcg(a.props + 2) : 0.0;
+                    p0 += d0; p1 += d1; p2 += d2;
+                    my2 = fma(d0, d0, my2); my2 = fma(d1, d1, my2); my2 = fma(d2, d2, my2);
                 }
-                double tot = block_sum(part, red);
-                if (tid == 0) s1[j] = tot;
+                for (int o = 16; o > 0; o >>= 1) {
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                    p2 += __shfl_xor_sync(0xffffffffu, p2, o); my2 += __shfl_xor_sync(0xffffffffu, my2, o);
+                }
+                __syncthreads();
+                if ((tid & 31) == 0) { int w = tid >> 5; sred4[w] = p0; sred4[32 + w] = p1; sred4[64 + w] = p2; sred4[96 + w] = my2; }
+                __syncthreads();
+                if (tid < 4) { double t = 0.0; for (int w = 0; w < (ACCEPT_THREADS >> 5); ++w) t += sred4[tid * 32 + w]; s1[tid] = t; }
+                __syncthreads();
+                my2 = s1[3];
+            } else {
+                for (int j = 0; j < dim; ++j) {
+                    double part = 0.0;
+                    for (int p = tid; p < P; p += ACCEPT_THREADS) {
+                        double d = (double)a.props[(long long)p * dim + j] - (double)a.props[j];
+                        part += d; my2 = fma(d, d, my2);
+                    }
+                    double tot = block_sum(part, red);
+                    if (tid == 0) s1[j] = tot;
+                }
+                my2 = block_sum(my2, red);
+                __syncthreads();
             }
-            double S2 = block_sum(my2, red);
-            __syncthreads();
+            const double S2 = my2;
             for (int p = tid; p < P; p += ACCEPT_THREADS) {
                 double dj2 = 0.0, dot = 0.0;
                 for (int j = 0; j < dim; ++j) {
@@ -225,15 +261,15 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
                 double sumsq = (double)P * dj2 - 2.0 * dot + S2;
                 double kt;
                 if (cfg.flags & PMP_FLAG_KERNEL_MEAN)   // MP_FC.py:107-114: sum_k mean_dim(logK_jk) / P, k != j (tran[j][j] = 0)
-                    kt = ((double)(P - 1) * (-HALF_LOG_2PI - log(ks)) - 0.5 * sumsq / (ks * ks) / (double)dim) / (double)P;
+                    kt = ((double)(P - 1) * log_norm_k - half_inv_ks2 * sumsq / (double)dim) / (double)P;
                 else
-                    kt = (double)(P - 1) * dim * (-HALF_LOG_2PI - log(ks)) - 0.5 * sumsq / (ks * ks);
+                    kt = (double)(P - 1) * dim * log_norm_k - half_inv_ks2 * sumsq;
                 A[p] = lt[p] + kt;
             }
         } else {
             for (int p = tid; p < P; p += ACCEPT_THREADS) A[p] = lt[p] + (use_kernel ? a.logw[p] : 0.0);  // kernel term precomputed into logw
         }
-    } else if (cfg.algo == PMP_ALGO_PSP) {
+    } else if constexpr (ALGO == PMP_ALGO_PSP) {
         // binary tree Barker product (lb.py:216-240): m = a mod 2^(c+1), partner q = m xor 2^c.  K is symmetric so
         // log(w_new/(w_new+w_old)) = logsigmoid(lt[m] - lt[q]).
         for (int p = tid; p < P; p += ACCEPT_THREADS) {
@@ -244,7 +280,7 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
             }
             A[p] = s;
         }
-    } else if (cfg.algo == PMP_ALGO_PMP) {
+    } else if constexpr (ALGO == PMP_ALGO_PMP) {
         // general tree (lb.py:315-330): level i, stride s = b^i, group h < s = {h + j s}; A[h + j s] += log softmax_j(v),
         // v_j = lt + sum_{k != j} log K; then nodes [b^(i+1), b^(i+2)) inherit A[x mod b^(i+1)] (or the reference's
         // typo modulus b*(i+1) under PMP_FLAG_QUIRK_LEVEL_MOD).
@@ -305,10 +341,11 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
         __syncthreads();
     }
     for (int p = tid; p < P; p += ACCEPT_THREADS) a.logw[p] = A[p];
+    PMP_STAMP(dbg, 2);
 
     // ---- 3. draw -------------------------------------------------------------------------------------------
     int n_draws;
-    if (cfg.algo == PMP_ALGO_MH || cfg.algo == PMP_ALGO_BARKER) {
+    if constexpr (ALGO == PMP_ALGO_MH) {
         n_draws = 1;
         if (tid == 0) {
             double u = a.uniforms ? a.uniforms[0] : u64_to_unit(stream_u64(a.seed, iter, STREAM_DRAW, 0));
@@ -324,17 +361,19 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
         mx = block_max(mx, red);
         for (int p = tid; p < P; p += ACCEPT_THREADS) { double w = exp(A[p] - mx); A[p] = (w == w) ? w : 0.0; }
         __syncthreads();
+        PMP_STAMP(dbg, 3);
         block_inclusive_scan(A, P, red);
         const double total = A[P - 1];
-        __syncthreads();
-        for (int p = tid; p < P; p += ACCEPT_THREADS) A[p] = A[p] / total;
-        __syncthreads();
+        PMP_STAMP(dbg, 4);
+        // inverse-CDF draws on the unnormalised cdf: first k with cdf_k > u*total ('right', numpy) or >= ('left', libstdc++);
+        // same index as normalising first except for u within an ulp of a boundary (oracle mirror: draw_blocked)
         n_draws = (cfg.draw == PMP_DRAW_SINGLE) ? 1 : P;
         const bool right = (cfg.draw != PMP_DRAW_CUDA);
         for (int t = tid; t < n_draws; t += ACCEPT_THREADS) {
             double u = a.uniforms ? a.uniforms[t] : u64_to_unit(stream_u64(a.seed, iter, STREAM_DRAW, (unsigned long long)t));
-            int lo = 0, hi = P;   // first index with cdf > u (right) or cdf >= u (left)
-            while (lo < hi) { int mid = (lo + hi) >> 1; bool go = right ? (A[mid] <= u) : (A[mid] < u); if (go) lo = mid + 1; else hi = mid; }
+            const double thr = u * total;
+            int lo = 0, hi = P;
+            while (lo < hi) { int mid = (lo + hi) >> 1; bool go = right ? (A[mid] <= thr) : (A[mid] < thr); if (go) lo = mid + 1; else hi = mid; }
             a.draws[t] = min(lo, P - 1);
         }
         __syncthreads();
@@ -350,6 +389,7 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
         __syncthreads();
     }
     const int next = s_next;
+    PMP_STAMP(dbg, 5);
 
     // ---- 4. state, trace, counters -------------------------------------------------------------------------
     if (!a.advance) { if (tid == 0) a.cnt->last_next = next; return; }
@@ -373,6 +413,38 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(AcceptArgs a)
         a.cnt->iteration = iter + 1;
         a.cnt->last_next = next;
     }
+    PMP_STAMP(dbg, 6);
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(const __grid_constant__ AcceptArgs a) {
+    extern __shared__ double accept_sm[];
+    accept_device<ALGO>(a, accept_sm);
+}
+
+// Standard normals of one iteration as float32: z[(iter & 1) * P*dim + node*dim + j].  The fused sweep fills the other
+// half for iteration+1 while it runs (they depend on counters only, never on the chain state).
+__global__ void __launch_bounds__(256) gen_normals_kernel(float* z, const DeviceCounters* cnt, unsigned long long seed, int count, int ahead) {
+    const unsigned long long iter = cnt->iteration + (unsigned long long)ahead;
+    float* dst = z + (iter & 1) * (long long)count;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x)
+        dst[e] = (float)stream_normal(seed, iter, STREAM_PROPOSAL, (unsigned long long)e);
+}
+
+// proposal_value with the normals read from a prefetched table instead of being generated in place
+__device__ __forceinline__ float proposal_value_z(const ProposeArgs& a, const float* __restrict__ z, int node, int j, float v) {
+    if (a.tree == PMP_TREE_FLAT) {
+        if (node > 0) v = __fadd_rn(v, __fmul_rn(a.alpha, z[(long long)node * a.dim + j]));
+        return v;
+    }
+    const int b = (a.tree == PMP_TREE_BINARY) ? 2 : a.b;
+    long long s = 1;
+    for (int l = 0; l < a.depth; ++l) {
+        long long digit = (node / s) % b;
+        if (digit != 0) { long long anc = node % (s * b); v = __fadd_rn(v, __fmul_rn(a.alpha, z[anc * a.dim + j])); }
+        s *= b;
+    }
+    return v;
 }
 
 }  // namespace pmp

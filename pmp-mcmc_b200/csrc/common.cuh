@@ -82,6 +82,11 @@ struct pmp_ctx {
     int32_t* d_draws = nullptr;        // [P]
     double* d_uniforms = nullptr;      // [P+1] injected uniforms
     pmp::DeviceCounters* d_cnt = nullptr;
+    float* d_z = nullptr;              // [2, P*dim] prefetched standard normals (current / next iteration)
+    unsigned long long* d_dbg = nullptr; // optional phase stamps
+    unsigned int* d_done = nullptr;    // CTA completion counter of the fused sweep+accept kernel
+    unsigned long long host_iter = 0;  // host mirror of d_cnt->iteration
+    long long z_valid_iter = -1;       // iteration whose normals are in d_z, -1: none
     bool lt_valid = false;             // d_lt holds the log-targets of the current proposals
     bool acc_pending = false;          // d_acc holds an un-finalised sweep
 
@@ -90,6 +95,7 @@ struct pmp_ctx {
     // graph cache for pmp_run
     cudaGraphExec_t graph_exec = nullptr;
     int graph_iters = 0;
+    long long graph_launches_total = 0;
 
     // misc
     void* d_flush = nullptr; size_t flush_bytes = 0;

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "accept.cuh"
+#include "accept_fast.cuh"
 #include "common.cuh"
 #include "sweep_linear.cuh"
 
@@ -84,24 +85,41 @@ static int launch_propose(pmp_ctx* c) {
     return PMP_OK;
 }
 
-static int launch_sweep_linear(pmp_ctx* c) {
+static size_t sweep_smem_bytes() { return (size_t)2 * TILE_CHUNKS * CHUNK_STRIDE * sizeof(float); }
+
+static AcceptArgs make_accept_args(pmp_ctx* c, int from_acc, int only_finalize, int advance, const double* d_uniforms) {
+    AcceptArgs a{};
+    a.cfg = c->cfg; a.P = c->P; a.n_global = c->n_global; a.state = c->d_state; a.props = c->d_props; a.acc = c->d_acc;
+    a.lt = c->d_lt; a.logw = c->d_logw; a.draws = c->d_draws; a.uniforms = d_uniforms; a.cnt = c->d_cnt; a.seed = c->seed;
+    a.sat_limit = sat_limit(c); a.inv_scale = 1.0 / (double)c->cfg.scale; a.dbg = c->d_dbg; a.from_acc = from_acc; a.only_finalize = only_finalize; a.advance = advance; a.trace = c->trace;
+    return a;
+}
+
+// generate: also fill the next iteration's half of the normals table as a side job.
+static int launch_sweep_linear(pmp_ctx* c, int generate) {
     PMP_REQUIRE(c->d_x && c->n_local >= 0, "linear-Gaussian data not set (pmp_set_data_linear)");
     constexpr int R = 4;
     int need = (c->P + R - 1) / R;
-    int TP = 1; while (TP < need && TP < SWEEP_THREADS) TP <<= 1;
+    int tp_cap = env_int("PMP_SWEEP_TP", 32);
+    if (tp_cap > MAX_TP) tp_cap = MAX_TP;
+    int TP = 1; while (TP < need && TP < tp_cap) TP <<= 1;
     int TD = SWEEP_THREADS / TP;
     long long nchunks = (c->n_local + CHUNK - 1) / CHUNK;
     if (nchunks == 0) return PMP_OK;
-    int gy = (c->P + TP * R - 1) / (TP * R);
-    int per_sm = env_int("PMP_SWEEP_BLOCKS_PER_SM", 4);
-    long long gx = ((long long)c->sm_count * per_sm + gy - 1) / gy;
-    long long want = (nchunks + TD - 1) / TD;
+    int ntiles = (c->P + TP * R - 1) / (TP * R);
+    long long units = (long long)ntiles * nchunks;
+    int per_sm = env_int("PMP_SWEEP_BLOCKS_PER_SM", 2);
+    long long gx = (long long)c->sm_count * per_sm;
+    int rounds = env_int("PMP_SWEEP_ROUNDS", 0);      // > 0: fixed chunks per data-thread per CTA (many small CTAs)
+    if (rounds > 0) gx = (units + (long long)rounds * TD - 1) / ((long long)rounds * TD);
+    long long want = (units + TD - 1) / TD;          // at least TD chunks per CTA so every data-thread has work
     if (gx > want) gx = want;
     if (gx < 1) gx = 1;
-    SweepArgs a{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, TP, TD, sat_limit(c)};
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    if (env_int("PMP_SWEEP_SCALAR", 0)) sweep_linear_kernel<R, false><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
-    else sweep_linear_kernel<R, true><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    SweepArgs a{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, TP, TD, sat_limit(c), generate, c->d_z,
+                ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha},
+                c->d_dbg};
+    if (env_int("PMP_SWEEP_SCALAR", 0)) sweep_linear_kernel<R, false><<<(unsigned)gx, SWEEP_THREADS, sweep_smem_bytes(), c->stream>>>(a);
+    else sweep_linear_kernel<R, true><<<(unsigned)gx, SWEEP_THREADS, sweep_smem_bytes(), c->stream>>>(a);
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
@@ -114,33 +132,69 @@ static int allreduce_acc(pmp_ctx* c) {
 }
 
 static int launch_accept(pmp_ctx* c, int from_acc, int only_finalize, int advance, const double* d_uniforms) {
-    AcceptArgs a{};
-    a.cfg = c->cfg; a.P = c->P; a.n_global = c->n_global; a.state = c->d_state; a.props = c->d_props; a.acc = c->d_acc;
-    a.lt = c->d_lt; a.logw = c->d_logw; a.draws = c->d_draws; a.uniforms = d_uniforms; a.cnt = c->d_cnt; a.seed = c->seed;
-    a.sat_limit = sat_limit(c); a.from_acc = from_acc; a.only_finalize = only_finalize; a.advance = advance; a.trace = c->trace;
+    AcceptArgs a = make_accept_args(c, from_acc, only_finalize, advance, d_uniforms);
     size_t smem = (size_t)c->P * 2 * sizeof(double);
-    accept_kernel<<<1, ACCEPT_THREADS, smem, c->stream>>>(a);
+    switch (c->cfg.algo) {
+        case PMP_ALGO_MH: case PMP_ALGO_BARKER: accept_kernel<PMP_ALGO_MH><<<1, ACCEPT_THREADS, smem, c->stream>>>(a); break;
+        case PMP_ALGO_MP: accept_kernel<PMP_ALGO_MP><<<1, ACCEPT_THREADS, smem, c->stream>>>(a); break;
+        case PMP_ALGO_PSP: accept_kernel<PMP_ALGO_PSP><<<1, ACCEPT_THREADS, smem, c->stream>>>(a); break;
+        case PMP_ALGO_PMP: accept_kernel<PMP_ALGO_PMP><<<1, ACCEPT_THREADS, smem, c->stream>>>(a); break;
+        default: accept_kernel<PMP_ALGO_TABLE><<<1, ACCEPT_THREADS, smem, c->stream>>>(a); break;
+    }
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+static bool fast_accept_ok(const pmp_ctx* c) {
+    if (c->cfg.target != PMP_TARGET_LINEAR_GAUSS || env_int("PMP_ACCEPT_GENERIC", 0)) return false;
+    if ((size_t)c->P * (c->cfg.algo == PMP_ALGO_PSP ? 32 : 16) > 220 * 1024) return false;
+    if (c->cfg.algo == PMP_ALGO_MP || c->cfg.algo == PMP_ALGO_PSP) return true;
+    return c->cfg.algo == PMP_ALGO_TABLE && ((c->cfg.flags & (PMP_FLAG_QUIRK_TABLE_CONST | PMP_FLAG_NO_KERNEL_TERM)) != 0) && !(c->cfg.flags & PMP_FLAG_STANDARDIZE);
+}
+
+static int launch_accept_fast(pmp_ctx* c, int make_next) {
+    AcceptFastArgs fa{make_accept_args(c, 1, 0, 1, nullptr), c->d_z, make_next,
+                      ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha}};
+    size_t smem = (size_t)c->P * (c->cfg.algo == PMP_ALGO_PSP ? 4 : 2) * sizeof(double);
+    switch (c->cfg.algo) {
+        case PMP_ALGO_MP: accept_fast_kernel<PMP_ALGO_MP><<<1, ACCEPT_THREADS, smem, c->stream>>>(fa); break;
+        case PMP_ALGO_PSP: accept_fast_kernel<PMP_ALGO_PSP><<<1, ACCEPT_THREADS, smem, c->stream>>>(fa); break;
+        default: accept_fast_kernel<PMP_ALGO_TABLE><<<1, ACCEPT_THREADS, smem, c->stream>>>(fa); break;
+    }
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
 }
 
 // one full iteration on the stream: propose → sweep → [all-reduce] → accept
-static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sweep_end) {
+static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sweep_end, bool first_of_graph) {
     int rc;
-    if ((rc = launch_propose(c))) return rc;
     if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS) {
+        // fused chain loop: the acceptance kernel of iteration i publishes the nodes of iteration i+1 from the normals
+        // table that the sweep of iteration i filled as a side job; only the first iteration of a run (or of a captured
+        // graph, which cannot know what preceded it) builds its table and nodes with the stand-alone kernels.
+        const int fused = env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c) && c->world == 1;
+        const bool chained = fused && !first_of_graph && c->z_valid_iter == (long long)c->host_iter;
+        if (!chained && (rc = launch_propose(c))) return rc;
         if (sweep_begin) PMP_CUDA(cudaEventRecord(sweep_begin, c->stream));
-        if ((rc = launch_sweep_linear(c))) return rc;
+        if ((rc = launch_sweep_linear(c, fused))) return rc;
         if (sweep_end) PMP_CUDA(cudaEventRecord(sweep_end, c->stream));
         if ((rc = allreduce_acc(c))) return rc;
-        return launch_accept(c, 1, 0, 1, nullptr);
+        if (fast_accept_ok(c)) { if ((rc = launch_accept_fast(c, fused))) return rc; }
+        else if ((rc = launch_accept(c, 1, 0, 1, nullptr))) return rc;
+        c->host_iter++;
+        c->z_valid_iter = fused ? (long long)c->host_iter : -1;
+        return PMP_OK;
     }
+    if ((rc = launch_propose(c))) return rc;
     if (c->cfg.target == PMP_TARGET_FC || c->cfg.target == PMP_TARGET_EXTERNAL) {
         set_error("pmp_run: target %d needs host-driven log-targets (use pmp_propose / pmp_write_logtarget / pmp_accept)", c->cfg.target);
         return PMP_ERR_UNSUPPORTED;
     }
-    return launch_accept(c, 0, 0, 1, nullptr);
+    if ((rc = launch_accept(c, 0, 0, 1, nullptr))) return rc;
+    c->host_iter++;
+    return PMP_OK;
 }
 
 }  // namespace pmp
@@ -184,7 +238,23 @@ int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* 
     PMP_CUDA(cudaEventCreate(&c->ev0)); PMP_CUDA(cudaEventCreate(&c->ev1));
     PMP_CUDA(cudaMalloc((void**)&c->d_cnt, sizeof(DeviceCounters)));
     PMP_CUDA(cudaMemset(c->d_cnt, 0, sizeof(DeviceCounters)));
-    PMP_CUDA(cudaFuncSetAttribute(accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_NODES * 2 * (int)sizeof(double)));
+    if (env_int("PMP_DEBUG_STAMPS", 0)) { PMP_CUDA(cudaMalloc((void**)&c->d_dbg, (64 + 3 * 1024) * 8)); PMP_CUDA(cudaMemset(c->d_dbg, 0, (64 + 3 * 1024) * 8)); }
+    PMP_CUDA(cudaMalloc((void**)&c->d_done, sizeof(unsigned int)));
+    PMP_CUDA(cudaMemset(c->d_done, 0, sizeof(unsigned int)));
+    const int accept_smem = MAX_NODES * 2 * (int)sizeof(double);
+    PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_PSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_PMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(sweep_linear_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes()));
+    PMP_CUDA(cudaFuncSetAttribute(sweep_linear_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes()));
+    // without this the driver may pick a carveout that fits a single CTA per SM
+    PMP_CUDA(cudaFuncSetAttribute(sweep_linear_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PMP_CUDA(cudaFuncSetAttribute(sweep_linear_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PMP_CUDA(cudaFuncSetAttribute(accept_fast_kernel<PMP_ALGO_MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_fast_kernel<PMP_ALGO_PSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * accept_smem > 220 * 1024 ? 220 * 1024 : 2 * accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_fast_kernel<PMP_ALGO_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
     if (world_size > 1) {
         PMP_REQUIRE(nccl_unique_id, "world_size > 1 needs an NCCL unique id");
         int rc = load_nccl(); if (rc) { delete c; return rc; }
@@ -208,7 +278,7 @@ int pmp_destroy(pmp_ctx* c) {
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
                     c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush,
-                    c->d_chain_states, c->d_chain_samples};
+                    c->d_chain_states, c->d_chain_samples, c->d_z, c->d_done};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -269,6 +339,8 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     if ((rc = dev_alloc(&c->d_logw, (size_t)P))) return rc;
     if ((rc = dev_alloc(&c->d_draws, (size_t)P))) return rc;
     if ((rc = dev_alloc(&c->d_uniforms, (size_t)P + 1))) return rc;
+    if ((rc = dev_alloc(&c->d_z, (size_t)2 * P * cfg->dim))) return rc;
+    c->z_valid_iter = -1;
     PMP_CUDA(cudaMemset(c->d_acc, 0, P * sizeof(unsigned long long)));
     PMP_CUDA(cudaMemset(c->d_props, 0, (size_t)P * cfg->dim * sizeof(float)));
     PMP_CUDA(cudaMemset(c->d_lt, 0, P * sizeof(double)));
@@ -329,6 +401,7 @@ int pmp_seed(pmp_ctx* c, uint64_t seed, uint64_t iteration) {
     PMP_CUDA(cudaStreamSynchronize(c->stream));
     if (seed != c->seed) drop_graph(c);   // the key is a baked kernel argument
     c->seed = seed;
+    c->host_iter = iteration; c->z_valid_iter = -1;
     unsigned long long it = iteration;
     PMP_CUDA(cudaMemcpyAsync(&c->d_cnt->iteration, &it, sizeof(it), cudaMemcpyHostToDevice, c->stream));
     PMP_CUDA(cudaStreamSynchronize(c->stream));
@@ -375,7 +448,7 @@ int pmp_loglik(pmp_ctx* c, double* out_host) {
     PMP_CUDA(cudaSetDevice(c->device));
     int rc;
     if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS) {
-        if ((rc = launch_sweep_linear(c))) return rc;
+        if ((rc = launch_sweep_linear(c, 0))) return rc;
         if ((rc = allreduce_acc(c))) return rc;
         if ((rc = launch_accept(c, 1, 1, 0, nullptr))) return rc;
     } else if (c->cfg.target == PMP_TARGET_FC) {
@@ -420,6 +493,7 @@ int pmp_accept(pmp_ctx* c, const double* uniforms, int64_t n_uniforms, int32_t* 
     int rc = launch_accept(c, 0, 0, 1, d_u);
     if (rc) return rc;
     c->lt_valid = false;
+    c->host_iter++;
     if (idx_out || next_out || uniforms) {
         int nd = (c->cfg.algo == PMP_ALGO_MH || c->cfg.algo == PMP_ALGO_BARKER || c->cfg.draw == PMP_DRAW_SINGLE) ? 1 : c->P;
         if (idx_out) PMP_CUDA(cudaMemcpyAsync(idx_out, c->d_draws, nd * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -497,21 +571,30 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
         if (!c->graph_exec || c->graph_iters != GI) {
             drop_graph(c);
             cudaGraph_t graph;
+            const long long launches_before = c->launches;
+            const unsigned long long iter_before = c->host_iter;
+            const long long zvalid_before = c->z_valid_iter;
             PMP_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             rc = PMP_OK;
-            for (int i = 0; i < GI && rc == PMP_OK; ++i) rc = enqueue_iteration(c, nullptr, nullptr);
+            for (int i = 0; i < GI && rc == PMP_OK; ++i) rc = enqueue_iteration(c, nullptr, nullptr, i == 0);
             cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-            if (rc) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+            if (rc) { if (e == cudaSuccess) cudaGraphDestroy(graph); c->host_iter = iter_before; c->z_valid_iter = zvalid_before; return rc; }
             PMP_CUDA(e);
             PMP_CUDA(cudaGraphInstantiate(&c->graph_exec, graph, 0));
             cudaGraphDestroy(graph);
             c->graph_iters = GI;
-            c->launches -= (long long)GI * (c->cfg.target == PMP_TARGET_LINEAR_GAUSS ? 3 : 2);   // capture enqueues are not launches
+            c->graph_launches_total = c->launches - launches_before;
+            c->launches = launches_before;   // enqueues during capture are not launches
+            c->host_iter = iter_before; c->z_valid_iter = zvalid_before;
         }
-        const long long per_iter = (c->cfg.target == PMP_TARGET_LINEAR_GAUSS ? 3 : 2);
-        for (; done + GI <= iters; done += GI) { PMP_CUDA(cudaGraphLaunch(c->graph_exec, c->stream)); c->launches += per_iter * GI; }
+        for (; done + GI <= iters; done += GI) {
+            PMP_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+            c->launches += c->graph_launches_total;
+            c->host_iter += GI;
+            c->z_valid_iter = (env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c) && c->world == 1) ? (long long)c->host_iter : -1;
+        }
     }
-    for (; done < iters; ++done) if ((rc = enqueue_iteration(c, nullptr, nullptr))) return rc;
+    for (; done < iters; ++done) if ((rc = enqueue_iteration(c, nullptr, nullptr, false))) return rc;
     c->lt_valid = false;
     return PMP_OK;
 }
@@ -544,7 +627,7 @@ int pmp_run_timed(pmp_ctx* c, int64_t iters, float* total_ms, float* sweep_ms) {
         PMP_REQUIRE(iters <= 4096, "sweep timing mode supports <= 4096 iterations per call");
         while ((int64_t)c->ev_pool.size() < 2 * iters) { cudaEvent_t ev; PMP_CUDA(cudaEventCreate(&ev)); c->ev_pool.push_back(ev); }
         PMP_CUDA(cudaEventRecord(c->ev0, c->stream));
-        for (int64_t i = 0; i < iters; ++i) if ((rc = enqueue_iteration(c, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]))) return rc;
+        for (int64_t i = 0; i < iters; ++i) if ((rc = enqueue_iteration(c, c->ev_pool[2 * i], c->ev_pool[2 * i + 1], false))) return rc;
         PMP_CUDA(cudaEventRecord(c->ev1, c->stream));
         PMP_CUDA(cudaStreamSynchronize(c->stream));
         double acc = 0.0;
@@ -583,6 +666,13 @@ int pmp_fp32_peak(pmp_ctx* c, int packed, double* tflops) {
     }
     cudaFree(d_out);
     *tflops = best;
+    return PMP_OK;
+}
+
+int pmp_debug_stamps(pmp_ctx* c, unsigned long long* out64) {
+    PMP_REQUIRE(c && out64 && c->d_dbg, "debug stamps not enabled (PMP_DEBUG_STAMPS=1 before pmp_create)");
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    PMP_CUDA(cudaMemcpy(out64, c->d_dbg, (64 + 3 * 1024) * 8, cudaMemcpyDeviceToHost));
     return PMP_OK;
 }
 

@@ -13,6 +13,7 @@
 //     in which CTAs, or GPUs, contribute.
 // Roofline: FP32 issue.  3 FP32 lane-ops per (node, point) = 6 flop; nothing else scales with P*n.
 #pragma once
+#include "accept.cuh"
 #include "common.cuh"
 
 namespace pmp {
@@ -29,10 +30,15 @@ struct SweepArgs {
     int TP;                               // threads along the node axis (power of two, <= 256)
     int TD;                               // 256 / TP: threads along the chunk axis
     double sat_limit;                     // per-partial saturation bound in fixed-point units
+    int generate;                         // 1: also fill the next iteration's half of the normals table z (side job)
+    float* z;                             // [2, P*3] normals table: half (iter & 1) is the current iteration's, the other is filled here
+    ProposeArgs gen;
+    unsigned long long* dbg;              // optional phase stamps of CTA 0: [0..15] clock64, [16..31] globaltimer
 };
 
 constexpr int SWEEP_THREADS = 256;
-constexpr int TILE_CHUNKS = 32;                    // chunks staged per shared-memory tile (2048 points)
+constexpr int TILE_CHUNKS = 32;                    // chunks staged per shared-memory buffer (3072 points, 24.75 KB)
+constexpr int MAX_TP = 64;                         // node tile <= 256 nodes
 constexpr int CHUNK_STRIDE = 2 * CHUNK + 4;        // floats per staged chunk: x[CHUNK], y[CHUNK], 16 B pad (bank skew)
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -130,94 +136,153 @@ __device__ __forceinline__ void chunk_sumsq(const float* __restrict__ sx, const 
     }
 }
 
+// cp.async (LDGSTS) 16-byte copy; src_bytes = 0 zero-fills the destination without touching global memory
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Work decomposition.  A unit is (node tile, chunk): PT = TP*R nodes x CHUNK points.  Units are ordered tile-major and
+// cut into gridDim.x equal contiguous ranges, so every CTA (and therefore every SM) gets the same amount of FP32 work
+// to within one unit, for any P and n.  A range touches one tile, or two when it straddles a tile boundary; each
+// (tile, chunk range) segment ends with ONE integer atomic per node of the tile — P*gridDim.x/ntiles atomics per sweep
+// instead of P per CTA.  The chunks of a segment are staged with cp.async into a double-buffered shared-memory tile;
+// the first stage is issued before anything that depends on the chain state, so its latency hides behind the
+// construction of the tile's nodes.
 template <int R, bool PACKED>
-__global__ void __launch_bounds__(SWEEP_THREADS) sweep_linear_kernel(SweepArgs a) {
-    __shared__ __align__(16) float tile[TILE_CHUNKS * CHUNK_STRIDE];
-    __shared__ unsigned long long sacc[SWEEP_THREADS * R];   // used when TD > 1
+__global__ void __launch_bounds__(SWEEP_THREADS, 3) sweep_linear_kernel(const __grid_constant__ SweepArgs a) {
+    extern __shared__ __align__(16) float tile[];                 // 2 x TILE_CHUNKS x CHUNK_STRIDE floats
+    __shared__ float sprops[MAX_TP * R * 3];                      // the tile's nodes (b0, b1, sigma)
+    __shared__ double sscl[MAX_TP * R];                           // 2^FX_SHIFT / sigma^2 per node
 
     const int tid = threadIdx.x;
     const int tp = tid & (a.TP - 1);
     const int td = tid / a.TP;
-    const int node0 = (blockIdx.y * a.TP + tp) * R;
-
-    float b0[R], b1[R];
-    double scl[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int p = node0 + r;
-        if (p < a.P) {
-            b0[r] = a.theta[3 * p]; b1[r] = a.theta[3 * p + 1];
-            double s = (double)a.theta[3 * p + 2];
-            scl[r] = (double)(1 << FX_SHIFT) / (s * s);
-        } else { b0[r] = 0.f; b1[r] = 0.f; scl[r] = 0.0; }
-    }
-    unsigned long long accq[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) accq[r] = 0ull;
+    const int PT = a.TP * R;
+    const int ntiles = (a.P + PT - 1) / PT;
+    const long long units = (long long)ntiles * a.nchunks;
+    long long u = (long long)blockIdx.x * units / gridDim.x;
+    const long long u_end = (long long)(blockIdx.x + 1) * units / gridDim.x;
+    const int zcount = a.P * 3;
     bool saturated = false;
+    bool first_segment = true;
+    unsigned long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
+    PMP_STAMP(dbg, 0);
+    unsigned long long cta_t0 = 0; unsigned smid = 0;
+    if (a.dbg && tid == 0) { cta_t0 = globaltimer_ns(); asm volatile("mov.u32 %0, %smid;" : "=r"(smid)); }
 
-    const long long c_begin = (long long)blockIdx.x * a.nchunks / gridDim.x;
-    const long long c_end = (long long)(blockIdx.x + 1) * a.nchunks / gridDim.x;
+    auto stage = [&](int buf, long long t0, int nct) {
+        float* base = tile + buf * (TILE_CHUNKS * CHUNK_STRIDE);
+        for (int i = tid; i < nct * (CHUNK / 2); i += SWEEP_THREADS) {      // CHUNK/4 x-vectors + CHUNK/4 y-vectors per chunk
+            int c = i / (CHUNK / 2), k = i - c * (CHUNK / 2);
+            bool isy = k >= CHUNK / 4;
+            int kk = isy ? k - CHUNK / 4 : k;
+            long long g = (t0 + c) * CHUNK + 4 * kk;
+            const float* src = (isy ? a.y : a.x) + (g < a.n_local ? g : 0);
+            cp_async16(base + c * CHUNK_STRIDE + (isy ? CHUNK : 0) + 4 * kk, src, g < a.n_local ? 16 : 0);
+        }
+        cp_async_commit();
+    };
 
-    for (long long t0 = c_begin; t0 < c_end; t0 += TILE_CHUNKS) {
-        const int nct = (int)min((long long)TILE_CHUNKS, c_end - t0);
-        // stage nct chunks: coalesced 16-byte loads, x then y of each chunk
-        for (int i = tid; i < nct * (CHUNK / 4); i += SWEEP_THREADS) {
-            int c = i / (CHUNK / 4), k = i - c * (CHUNK / 4);
-            long long g = (t0 + c) * CHUNK + 4 * k;
-            float4 xv, yv;
-            if (g + 3 < a.n_local) {
-                xv = __ldg(reinterpret_cast<const float4*>(a.x + g));
-                yv = __ldg(reinterpret_cast<const float4*>(a.y + g));
-            } else {
-                float tx[4], ty[4];
+    while (u < u_end) {
+        const int ptile = (int)(u / a.nchunks);
+        const long long c_begin = u - (long long)ptile * a.nchunks;
+        const long long c_end = min(a.nchunks, c_begin + (u_end - u));
+        const int node_base = ptile * PT;
+        const int ntl = (int)((c_end - c_begin + TILE_CHUNKS - 1) / TILE_CHUNKS);
+
+        __syncthreads();                       // previous segment is done with the tile buffers and sprops
+        stage(0, c_begin, (int)min((long long)TILE_CHUNKS, c_end - c_begin));
+
+        PMP_STAMP(dbg, 1);
+
+        // ---- the tile's nodes (published by the acceptance kernel / pmp_propose) and their fixed-point scale factors
+        for (int i = tid; i < PT * 3; i += SWEEP_THREADS) {
+            int node = node_base + i / 3, j = i - (i / 3) * 3;
+            float v = (node < a.P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
+            sprops[i] = v;
+            if (j == 2) sscl[i / 3] = (node < a.P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+        }
+        __syncthreads();
+        PMP_STAMP(dbg, 2);
+        float b0[R], b1[R];
+        double scl[R];
+        unsigned long long accq[R];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    bool ok = g + j < a.n_local;
-                    tx[j] = ok ? a.x[g + j] : 0.f; ty[j] = ok ? a.y[g + j] : 0.f;
+        for (int r = 0; r < R; ++r) {
+            int i = tp * R + r;
+            b0[r] = sprops[3 * i]; b1[r] = sprops[3 * i + 1];
+            scl[r] = sscl[i];
+            accq[r] = 0ull;
+        }
+
+        // ---- stream the segment's chunks through the double-buffered tile
+        for (int t = 0; t < ntl; ++t) {
+            const long long t0 = c_begin + (long long)t * TILE_CHUNKS;
+            const int nct = (int)min((long long)TILE_CHUNKS, c_end - t0);
+            if (t + 1 < ntl) {
+                stage((t + 1) & 1, t0 + TILE_CHUNKS, (int)min((long long)TILE_CHUNKS, c_end - t0 - TILE_CHUNKS));
+                cp_async_wait<1>();
+            } else cp_async_wait<0>();
+            __syncthreads();
+            if (t == 0) PMP_STAMP(dbg, 3);
+            const float* base = tile + (t & 1) * (TILE_CHUNKS * CHUNK_STRIDE);
+            for (int c = td; c < nct; c += a.TD) {
+                int cnt = (int)min((long long)CHUNK, a.n_local - (t0 + c) * CHUNK);
+                float part[R];
+                const float* sx = base + c * CHUNK_STRIDE;
+                chunk_sumsq<R, PACKED>(sx, sx + CHUNK, cnt, b0, b1, part);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double dq = (double)part[r] * scl[r];
+                    if (!(dq < a.sat_limit)) { dq = a.sat_limit; saturated = true; }
+                    accq[r] += (unsigned long long)__double2ll_rn(dq);
                 }
-                xv = make_float4(tx[0], tx[1], tx[2], tx[3]); yv = make_float4(ty[0], ty[1], ty[2], ty[3]);
             }
-            float* dst = tile + c * CHUNK_STRIDE;
-            reinterpret_cast<float4*>(dst)[k] = xv;
-            reinterpret_cast<float4*>(dst + CHUNK)[k] = yv;
+            if (t + 1 < ntl) __syncthreads();
         }
-        __syncthreads();
-        for (int c = td; c < nct; c += a.TD) {
-            long long first = (t0 + c) * CHUNK;
-            int cnt = (int)min((long long)CHUNK, a.n_local - first);
-            float part[R];
-            const float* sx = tile + c * CHUNK_STRIDE;
-            chunk_sumsq<R, PACKED>(sx, sx + CHUNK, cnt, b0, b1, part);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double dq = (double)part[r] * scl[r];
-                if (!(dq < a.sat_limit)) { dq = a.sat_limit; saturated = true; }
-                accq[r] += (unsigned long long)__double2ll_rn(dq);
-            }
-        }
-        __syncthreads();
-    }
 
-    if (a.TD > 1) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) sacc[tid * R + r] = 0ull;   // only slots [0, TP*R) are accumulated into
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (accq[r]) atomicAdd(&sacc[tp * R + r], accq[r]);
-        __syncthreads();
-        if (td == 0) {
+        PMP_STAMP(dbg, 4);
+        if (first_segment && a.generate) {
+            // side job of the last warp (it owns the fewest chunks) before it joins the flush: this CTA's slice of the
+            // normals of the NEXT iteration (they depend on counters only, never on the chain state), so that no launch
+            // ever waits for a binary64 quantile evaluation
+            const unsigned long long iter = a.gen.cnt->iteration;
+            const int per = (zcount + gridDim.x - 1) / gridDim.x;
+            const int k = SWEEP_THREADS - 1 - tid, e = blockIdx.x * per + k;
+            if (k < per && e < zcount)
+                a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_normal(a.gen.seed, iter + 1, STREAM_PROPOSAL, (unsigned long long)e);
+        }
+        first_segment = false;
+        // ---- segment flush, integer adds only: lanes that share a node (warp shuffles) → one row per warp in shared
+        // memory → one global atomic per node.  (64-bit shared atomics compile to CAS spin loops; not used.)
+        if (a.TP < 32) {
 #pragma unroll
             for (int r = 0; r < R; ++r)
-                if (node0 + r < a.P && sacc[tp * R + r]) atomicAdd(a.acc + node0 + r, sacc[tp * R + r]);
+                for (int o = 16; o >= a.TP; o >>= 1) accq[r] += __shfl_xor_sync(0xffffffffu, accq[r], o);
         }
-    } else {
+        __syncthreads();                       // everyone is done reading the data tile: reuse it as integer scratch
+        unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile);
+        const int lane = tid & 31, warp = tid >> 5;
+        const int rows = a.TP < 32 ? SWEEP_THREADS / 32 : a.TD;       // partial rows per node
+        const int row = a.TP < 32 ? warp : td;
+        if (a.TP >= 32 || lane < a.TP) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (node0 + r < a.P && accq[r]) atomicAdd(a.acc + node0 + r, accq[r]);
+            for (int r = 0; r < R; ++r) sred[row * PT + tp * R + r] = accq[r];
+        }
+        __syncthreads();
+        for (int i = tid; i < PT; i += SWEEP_THREADS) {
+            unsigned long long s = 0ull;
+            for (int k = 0; k < rows; ++k) s += sred[k * PT + i];
+            if (node_base + i < a.P && s) atomicAdd(a.acc + node_base + i, s);
+        }
+        u += c_end - c_begin;
+        PMP_STAMP(dbg, 5);
     }
     if (saturated) atomicOr(&a.cnt->flags, 1);
+    if (a.dbg && tid == 0 && blockIdx.x < 1024) { a.dbg[64 + 3 * blockIdx.x] = cta_t0; a.dbg[64 + 3 * blockIdx.x + 1] = globaltimer_ns(); a.dbg[64 + 3 * blockIdx.x + 2] = smid; }
 }
 
 // FP32 issue-rate microbenchmark: the denominator of the sweep's roofline (MEASURED_PEAKS.json has no FP32 number).

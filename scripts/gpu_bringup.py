@@ -5,7 +5,8 @@ import numpy as np
 import pmp_mcmc_b200 as pm
 from pmp_mcmc_b200 import _lib as L
 from oracle import oracle as o
-from tests.conftest import synthetic_linear
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from conftest import synthetic_linear
 
 c = pm.Context(0)
 print("device", c.device_info())
@@ -35,14 +36,17 @@ def bench(label, iters=2000):
     ms2, sw = c.run_timed(min(iters, 1000), sweep=True)
     print("%-40s %8.2f us/iter (graph)  | plain launches %8.2f us/iter, sweep kernel %7.2f us" % (label, ms / iters * 1e3, ms2 / min(iters, 1000) * 1e3, sw / min(iters, 1000) * 1e3), flush=True)
 
-for per_sm in (1, 2, 3, 4, 6, 8):
-    os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = str(per_sm)
-    for scalar in (0, 1):
-        os.environ["PMP_SWEEP_SCALAR"] = str(scalar)
+for tp in (16, 32, 64):
+    for per_sm in (2, 3):
+        os.environ["PMP_SWEEP_TP"] = str(tp); os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = str(per_sm)
         c.trace_config(0, 0)  # drops the cached graph
-        bench("P=1024 n=100k per_sm=%d %s" % (per_sm, "FFMA" if scalar else "FFMA2"))
-os.environ["PMP_SWEEP_SCALAR"] = "0"; os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = "4"
-for gi in (1, 8, 32, 128):
+        bench("P=1024 n=100k TP=%d per_sm=%d" % (tp, per_sm))
+os.environ["PMP_SWEEP_TP"] = "16"; os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = "3"
+os.environ["PMP_ACCEPT_GENERIC"] = "1"; c.trace_config(0, 0); bench("TP=16 per_sm=3 generic accept + propose kernels")
+os.environ["PMP_ACCEPT_GENERIC"] = "0"
+os.environ["PMP_SWEEP_SCALAR"] = "1"; c.trace_config(0, 0); bench("TP=16 per_sm=3 scalar FFMA")
+os.environ["PMP_SWEEP_SCALAR"] = "0"
+for gi in (1, 32):
     os.environ["PMP_GRAPH_ITERS"] = str(gi); c.trace_config(0, 0)
     bench("graph_iters=%d" % gi)
 os.environ["PMP_GRAPH_ITERS"] = "32"

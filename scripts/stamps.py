@@ -1,0 +1,26 @@
+import os, sys, ctypes
+os.environ["PMP_DEBUG_STAMPS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import pmp_mcmc_b200 as pm
+from pmp_mcmc_b200 import _lib as L
+from conftest import synthetic_linear
+for n, P in ((100000, 1024), (500, 4), (500, 1024)):
+    x, y = synthetic_linear(n)
+    c = pm.Context(0)
+    c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.01, scale=1000.0)
+    c.set_data_linear(x, y); c.set_state([1, 1, 1]); c.seed(1, 0)
+    c.run(320)
+    buf = (ctypes.c_uint64 * 64)()
+    c.L.pmp_debug_stamps.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    assert c.L.pmp_debug_stamps(c.h, buf) == 0
+    v = np.array(list(buf), dtype=np.int64)
+    sw_clk, sw_ns, ac_clk, ac_ns = v[0:6], v[16:22], v[32:39], v[48:55]
+    print("n=%d P=%d" % (n, P))
+    print("  sweep CTA0 phases (cycles): start→stage_issued %d →nodes_built %d →data_landed %d →compute_done %d →flushed %d" % tuple(np.diff(sw_clk)))
+    print("  sweep CTA0 start→end (globaltimer ns): %d" % (sw_ns[5] - sw_ns[0]))
+    print("  accept phases (cycles): start→lt %d →logw %d →max/exp %d →scan %d →draws %d →state/trace %d" % tuple(np.diff(ac_clk)))
+    print("  accept start→end ns: %d ; sweep CTA0 end → accept start ns: %d" % (ac_ns[6] - ac_ns[0], ac_ns[0] - sw_ns[5]))
+    print("  sweep CTA0 start → accept end ns: %d" % (ac_ns[6] - sw_ns[0]))
+    c.close()
