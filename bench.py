@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: multi-proposal MCMC on the 3-parameter linear-Gaussian model,
+P = 1024 candidate states per iteration, n = 100 000 data points (BASELINE.json metric; the reference's
+`100000_MP.cu` time-analysis shape: flat proposals, CUDA draw rule, SCALE 1000, alpha 0.01, theta0 = (1,1,1)).
+
+A "step" is one block of ITERS_PER_STEP chain iterations run device-resident (pmp_run).  Between steps L2 is flushed
+(256 MB memset); inside a step the 0.8 MB dataset is re-read from L2 by design — that is what a chain does.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); the dataset is sharded (strong scaling: n stays 100 000, as BASELINE
+config 3 names it) and the per-node partial sums are all-reduced with NCCL inside the library.
+`--impl reference` times the reference's CPU implementation of the same path (oracle port of lb.py's per-proposal
+torch loop; /root/reference cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_NODES = 1024
+N_DATA = 100000
+ITERS_PER_STEP = 1000
+SCALE = 1000.0
+ALPHA = 0.01
+METRIC = "proposal-evals/sec"
+UNIT = "proposal-evals/s"
+# README.md:44 of the reference (V100): MP, n=100000, P=1024: 33473.53 us kernel + 1099.258 us host/copy per iteration
+BASELINE_EVALS_PER_S = 1024 / ((33473.53 + 1099.258) * 1e-6)
+
+
+def synthetic(n, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    y = (-1.0 + 2.0 * x + 0.5 * rng.standard_normal(n)).astype(np.float32)
+    return x, y
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        while not self.stop_flag.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([c.strip() for c in line.split(",")])
+        p.terminate()
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_evals_per_s(x, y, n_evals, threads=None):
+    """The reference's CPU path for one sweep: a Python loop of BayesNet.loglik (lb.py:103-108, torch float32)."""
+    from oracle import oracle
+    import torch
+    rng = np.random.default_rng(1)
+    nets = (np.array([1, 1, 1], np.float32) + ALPHA * rng.standard_normal((n_evals, 3))).astype(np.float32)
+    oracle.loglik_lb_torch(x, y, nets[:8], threads)      # warm-up
+    t0 = time.perf_counter()
+    oracle.loglik_lb_torch(x, y, nets, threads)
+    dt = time.perf_counter() - t0
+    return n_evals / dt, torch.get_num_threads(), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    x, y = synthetic(N_DATA)
+    evals = 256          # bounded sample of the 1024-proposal sweep per step
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, cores, dt = cpu_port_evals_per_s(x, y, evals)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3 * (P_NODES / evals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32",
+            "data": "synthetic", "iters_per_sec": value / P_NODES,
+            "config": {"workload": "simple_net linear-Gaussian MP, P=1024, n=100000 (lb.py BayesNet.loglik per proposal on the host)", "P": P_NODES, "n": N_DATA},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d of the 1024 proposal-evaluations per step at n=100000, torch CPU float32 loop (oracle.loglik_lb_torch)" % evals},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--iters-per-step", type=int, default=ITERS_PER_STEP)
+    ap.add_argument("--weak", action="store_true", help="n = 100000 per GPU instead of 100000 in total")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    import torch
+    import pmp_mcmc_b200 as pm
+    from pmp_mcmc_b200 import _lib as L, dist as pdist
+    if world > 1:
+        import torch.distributed as td
+        torch.cuda.set_device(local)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pdist.create_context(local)
+    info = ctx.device_info()
+    iters = args.iters_per_step
+    n_global = N_DATA * world if args.weak else N_DATA
+    x, y = synthetic(n_global)
+    xp, yp = torch.from_numpy(x).pin_memory().numpy(), torch.from_numpy(y).pin_memory().numpy()     # pinned host buffers for the e2e arm
+
+    ctx.configure(L.TREE_FLAT, b=P_NODES, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=ALPHA, scale=SCALE)
+    lo, hi = pdist.set_data_linear_sharded(ctx, xp, yp)
+    ctx.set_state([1, 1, 1])
+    ctx.seed(2024, 0)
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: inputs already in HBM, CUDA events on the ctx stream, max over ranks -------------------
+    for _ in range(args.warmup):
+        ctx.l2_flush(); ctx.run(iters)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    for _ in range(args.steps):
+        ctx.l2_flush()
+        barrier()
+        ms, _ = ctx.run_timed(iters)
+        step_ms.append(max_over_ranks(ms))
+    barrier()
+    launches = ctx.launch_count() - launches0
+    total_s = sum(step_ms) * 1e-3
+    clocks = sampler.summary()
+    iters_per_s = args.steps * iters / total_s
+    value = iters_per_s * P_NODES
+
+    # ---- end-to-end arm: host buffers in, trace out, through the C-ABI the Python samplers call ----------------------
+    e2e_s = []
+    for s in range(2 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        pdist.set_data_linear_sharded(ctx, xp, yp)                 # H2D: this rank's shard of x and y
+        ctx.set_state([1, 1, 1]); ctx.seed(7, 0)
+        ctx.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT)
+        ctx.run(iters)
+        tr = ctx.read_trace()                                       # D2H: the chain ([iters,3] float32 + [iters] int32)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert tr["n"] == iters
+        if s >= 2:
+            e2e_s.append(dt)
+    e2e_value = args.steps * iters * P_NODES / sum(e2e_s)
+    h2d = int((hi - lo) * 8 + 12)
+    d2h = int(iters * 16)
+    ctx.trace_config(0, 0)
+
+    # ---- roofline of the dominant kernel (the sweep): algorithmic flops / average launch duration ---------------------
+    ctx.set_state([1, 1, 1]); ctx.seed(2024, 0); ctx.propose()
+    reps = 200
+    sweep_ms = ctx.time_sweep(reps) / reps
+    flops_per_launch = 6.0 * (hi - lo) * P_NODES                 # 3 FP32 lane-ops (sub, fma, fma) per (node, point), DESIGN.md §4
+    achieved = flops_per_launch / (sweep_ms * 1e-3) / 1e12
+    peak = max(ctx.fp32_peak(False), ctx.fp32_peak(True))         # measured FFMA/FFMA2 issue-rate microbenchmark (MEASURED_PEAKS.json has no FP32 figure)
+    bytes_per_launch = 8.0 * (hi - lo) + 12.0 * P_NODES + 8.0 * P_NODES
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured in this run by pmp_fp32_peak (FFMA/FFMA2 microbenchmark); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                "kernel": "sweep_linear_kernel<4,true>", "kernel_us": sweep_ms * 1e3, "flops_per_launch": flops_per_launch,
+                "hbm": {"achieved_gbs": bytes_per_launch / (sweep_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "note": "0.8 MB of data per launch: L2-resident, HBM is not the bound"}}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            v, cores, dt = cpu_port_evals_per_s(x, y, 2048)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "2048 proposal-evaluations at n=100000 (2 sweeps of P=1024) with the lb.py per-proposal torch loop, %.1f s" % dt}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
+                "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32", "data": "synthetic",
+                "iters_per_sec": iters_per_s, "us_per_iter": 1e6 / iters_per_s,
+                "config": {"workload": "simple_net linear-Gaussian multi-proposal MCMC (100000_MP.cu shape): P=1024 nodes, n=%d points, flat proposals alpha=0.01, SCALE=1000, CUDA draw rule" % n_global,
+                           "P": P_NODES, "n": n_global, "iters_per_step": iters, "device": info["name"],
+                           "l2": "flushed (256 MB memset) between steps; inside a step the dataset is re-read from L2 by design",
+                           "baseline": "reference README.md:44, V100: (33473.53 + 1099.258) us per iteration at P=1024, n=100000"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "what": "set_data (pinned host x,y) + set_state + %d iterations + read_trace per step, wall clock" % iters},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

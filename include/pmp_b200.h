@@ -86,6 +86,7 @@ typedef enum pmp_draw {
 #define PMP_FLAG_STANDARDIZE       4u  /* A=(A-mean)/std_unbiased before exp (PMP_FC.py:138-141, MP_FC.py:116-119)  */
 #define PMP_FLAG_KERNEL_MEAN       8u  /* MP kernel term = sum_k mean_dim logK / P (MP_FC.py:107-114) instead of sum */
 #define PMP_FLAG_NO_KERNEL_TERM   16u  /* drop the proposal-kernel term entirely (symmetric kernels in PSP cancel anyway) */
+#define PMP_FLAG_UNIFORM_PROPOSAL 32u  /* increments alpha*(2u-1), u ~ U[0,1): random.uniform(-alpha, alpha) of SP (error.py:27) */
 
 typedef struct pmp_config {
     int32_t tree;        /* pmp_tree   */
@@ -163,9 +164,17 @@ int pmp_trace_reset(pmp_ctx* ctx);
 /* Timing helpers for bench.py: CUDA events on the ctx stream. pmp_run_timed = pmp_run + device time of the whole
  * region; sweep_ms (nullable) = summed device time of the sweep kernel alone over the region. */
 int pmp_run_timed(pmp_ctx* ctx, int64_t iters, float* total_ms, float* sweep_ms);
+/* reps back-to-back launches of the sweep kernel on the current proposals between two CUDA events (no gaps: the GPU is
+ * the bottleneck); ms = total device time.  The partial sums are discarded. */
+int pmp_time_sweep(pmp_ctx* ctx, int reps, float* ms);
 int pmp_launch_count(pmp_ctx* ctx, int64_t* launches);   /* kernels launched by this ctx since creation */
 int pmp_fp32_peak(pmp_ctx* ctx, int packed, double* tflops); /* FFMA (packed=0) / FFMA2 (packed=1) issue-rate microbenchmark */
 int pmp_l2_flush(pmp_ctx* ctx);
+
+/* Host-side evaluation of the library's counter-based streams (same bits as the device): uniforms in [0,1) with 53 bits,
+ * standard normals in binary64.  stream: 0 proposal increments, 1 draw uniforms, 2 pick uniform, 3 chain initialisation. */
+int pmp_stream_uniforms(uint64_t seed, uint64_t iteration, uint32_t stream, uint64_t idx0, int64_t count, double* out);
+int pmp_stream_normals(uint64_t seed, uint64_t iteration, uint32_t stream, uint64_t idx0, int64_t count, double* out);
 
 /* ---- Batched independent chains on analytic targets (error.py SP/MP/PSP/PMP, com_dim.py PMP, banana) -------------
  * n_chains chains, each running the configured tree/algo/draw on PMP_TARGET_{NORMAL1D,BANANA,STDNORMAL}; states and

@@ -103,10 +103,11 @@ def num_nodes(tree, b, depth):
     return b if tree == TREE_FLAT else (2 ** depth if tree == TREE_BINARY else b ** depth)
 
 
-def propose(tree, b, depth, dim, alpha, state, seed, it):
+def propose(tree, b, depth, dim, alpha, state, seed, it, uniform=False):
     P = num_nodes(tree, b, depth)
     st = _f32(state)
     out = np.empty((P, dim), dtype=np.float32)
+    lib().oracle_set_uniform_steps(1 if uniform else 0)
     lib().oracle_propose(tree, b, depth, dim, ctypes.c_float(alpha), _fptr(st), seed, it, _fptr(out))
     return out
 

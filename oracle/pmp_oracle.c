@@ -114,18 +114,25 @@ void oracle_stream_uniforms(uint64_t seed, uint64_t iter, uint32_t stream, uint6
  *    tree 2: (N+1)-ary   conv_pmp.cu:182-197, lb.py:356-360, error.py:145-149 */
 static float step32(float parent, float alpha, double z) { volatile float inc = alpha * (float)z; return parent + inc; }
 
+static int g_uniform_steps = 0;   /* 1: increments alpha*(2u-1) — random.uniform(-alpha, alpha), error.py:27 */
+void oracle_set_uniform_steps(int on) { g_uniform_steps = on; }
+static double step_value(uint64_t seed, uint64_t iter, uint64_t idx) {
+    if (g_uniform_steps) return fma(2.0, oracle_u64_to_unit(oracle_stream_u64(seed, iter, 0, idx)), -1.0);
+    return oracle_stream_normal(seed, iter, 0, idx);
+}
+
 void oracle_propose(int tree, int b, int depth, int dim, float alpha, const float* state, uint64_t seed, uint64_t iter, float* props) {
     for (int j = 0; j < dim; ++j) props[j] = state[j];
     if (tree == 0) {
         for (int i = 1; i < b; ++i)
             for (int j = 0; j < dim; ++j)
-                props[(size_t)i * dim + j] = step32(props[j], alpha, oracle_stream_normal(seed, iter, 0, (uint64_t)i * dim + j));
+                props[(size_t)i * dim + j] = step32(props[j], alpha, step_value(seed, iter, (uint64_t)i * dim + j));
     } else if (tree == 1) {
         for (int l = 0; l < depth; ++l) {
             long jj = 1L << l;
             for (long k = 0; k < jj; ++k)
                 for (int j = 0; j < dim; ++j)
-                    props[(size_t)(k + jj) * dim + j] = step32(props[(size_t)k * dim + j], alpha, oracle_stream_normal(seed, iter, 0, (uint64_t)(k + jj) * dim + j));
+                    props[(size_t)(k + jj) * dim + j] = step32(props[(size_t)k * dim + j], alpha, step_value(seed, iter, (uint64_t)(k + jj) * dim + j));
         }
     } else {
         long temp = 1;
@@ -134,7 +141,7 @@ void oracle_propose(int tree, int b, int depth, int dim, float alpha, const floa
                 for (long k = 0; k < temp; ++k) {
                     long to = k + temp * (jn + 1);
                     for (int j = 0; j < dim; ++j)
-                        props[(size_t)to * dim + j] = step32(props[(size_t)k * dim + j], alpha, oracle_stream_normal(seed, iter, 0, (uint64_t)to * dim + j));
+                        props[(size_t)to * dim + j] = step32(props[(size_t)k * dim + j], alpha, step_value(seed, iter, (uint64_t)to * dim + j));
                 }
             temp *= b;
         }

@@ -15,7 +15,7 @@ TREE_FLAT, TREE_BINARY, TREE_BARY = 0, 1, 2
 TARGET_LINEAR_GAUSS, TARGET_NORMAL1D, TARGET_BANANA, TARGET_STDNORMAL, TARGET_FC, TARGET_EXTERNAL = range(6)
 ALGO_MH, ALGO_BARKER, ALGO_MP, ALGO_PSP, ALGO_PMP, ALGO_TABLE = range(6)
 DRAW_PYTHON, DRAW_CUDA, DRAW_SINGLE = range(3)
-FLAG_QUIRK_LEVEL_MOD, FLAG_QUIRK_TABLE_CONST, FLAG_STANDARDIZE, FLAG_KERNEL_MEAN, FLAG_NO_KERNEL_TERM = 1, 2, 4, 8, 16
+FLAG_QUIRK_LEVEL_MOD, FLAG_QUIRK_TABLE_CONST, FLAG_STANDARDIZE, FLAG_KERNEL_MEAN, FLAG_NO_KERNEL_TERM, FLAG_UNIFORM_PROPOSAL = 1, 2, 4, 8, 16, 32
 TRACE_STATE, TRACE_NEXT, TRACE_DRAWS, TRACE_SAMPLES, TRACE_LOGW = 1, 2, 4, 8, 16
 
 EXPORTS = [
@@ -24,7 +24,8 @@ EXPORTS = [
     "pmp_get_iteration", "pmp_propose", "pmp_read_proposals", "pmp_write_proposals", "pmp_loglik", "pmp_write_logtarget",
     "pmp_accept", "pmp_read_logweights", "pmp_trace_config", "pmp_run", "pmp_sync", "pmp_read_trace", "pmp_trace_reset",
     "pmp_run_timed", "pmp_launch_count", "pmp_fp32_peak", "pmp_l2_flush", "pmp_chains_create", "pmp_chains_run",
-    "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc",
+    "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
+    "pmp_stream_normals", "pmp_time_sweep",
 ]
 
 
@@ -94,6 +95,7 @@ def load():
     L.pmp_trace_reset.argtypes = [vp]
     L.pmp_run_timed.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     L.pmp_launch_count.argtypes = [vp, ctypes.POINTER(i64)]
+    L.pmp_time_sweep.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.pmp_fp32_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     L.pmp_l2_flush.argtypes = [vp]
     L.pmp_chains_create.argtypes = [vp, i64, vp]
@@ -102,10 +104,29 @@ def load():
     L.pmp_chains_read_samples.argtypes = [vp, vp, i64]
     L.pmp_chains_run_timed.argtypes = [vp, i64, i32, ctypes.POINTER(ctypes.c_float)]
     L.pmp_set_data_fc.argtypes = [vp, vp, vp, i64, i64, i64]
+    L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
+    L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
     if L.pmp_abi_version() != 1:
         raise PmpError("libpmp_b200.so ABI version mismatch")
     _lib = L
     return L
+
+
+def stream_uniforms(seed, iteration, stream, idx0, count):
+    """Host evaluation of the library's Philox stream (no GPU needed): `count` uniforms in [0,1)."""
+    out = np.empty(count, dtype=np.float64)
+    rc = load().pmp_stream_uniforms(seed, iteration, stream, idx0, count, ctypes.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise PmpError(load().pmp_last_error().decode())
+    return out
+
+
+def stream_normals(seed, iteration, stream, idx0, count):
+    out = np.empty(count, dtype=np.float64)
+    rc = load().pmp_stream_normals(seed, iteration, stream, idx0, count, ctypes.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise PmpError(load().pmp_last_error().decode())
+    return out
 
 
 def _ptr(a):
@@ -254,6 +275,11 @@ class Context:
         total, sw = ctypes.c_float(), ctypes.c_float()
         self._chk(self.L.pmp_run_timed(self.h, iters, ctypes.byref(total), ctypes.byref(sw) if sweep else None))
         return total.value, (sw.value if sweep else None)
+
+    def time_sweep(self, reps):
+        ms = ctypes.c_float()
+        self._chk(self.L.pmp_time_sweep(self.h, reps, ctypes.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         n = ctypes.c_int64()

@@ -28,7 +28,7 @@ __host__ __device__ __forceinline__ long long ipow(int b, int e) { long long r =
 
 struct ProposeArgs {
     const float* state; float* props; const DeviceCounters* cnt;
-    unsigned long long seed; int P, dim, tree, b, depth; float alpha;
+    unsigned long long seed; int P, dim, tree, b, depth; float alpha; int uniform;
 };
 
 // One thread per (node, coordinate).  The value is built along the node's ancestor chain in float32 with the
@@ -37,7 +37,7 @@ struct ProposeArgs {
 __device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long long iter, int node, int j, float v) {
     if (a.tree == PMP_TREE_FLAT) {
         if (node > 0) {
-            float z = (float)stream_normal(a.seed, iter, STREAM_PROPOSAL, (unsigned long long)node * a.dim + j);
+            float z = (float)stream_step(a.seed, iter, (unsigned long long)node * a.dim + j, a.uniform);
             v = __fadd_rn(v, __fmul_rn(a.alpha, z));
         }
         return v;
@@ -48,7 +48,7 @@ __device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long
         long long digit = (node / s) % b;
         if (digit != 0) {
             long long anc = node % (s * b);
-            float z = (float)stream_normal(a.seed, iter, STREAM_PROPOSAL, (unsigned long long)anc * a.dim + j);
+            float z = (float)stream_step(a.seed, iter, (unsigned long long)anc * a.dim + j, a.uniform);
             v = __fadd_rn(v, __fmul_rn(a.alpha, z));
         }
         s *= b;
@@ -424,11 +424,11 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(const __grid_
 
 // Standard normals of one iteration as float32: z[(iter & 1) * P*dim + node*dim + j].  The fused sweep fills the other
 // half for iteration+1 while it runs (they depend on counters only, never on the chain state).
-__global__ void __launch_bounds__(256) gen_normals_kernel(float* z, const DeviceCounters* cnt, unsigned long long seed, int count, int ahead) {
+__global__ void __launch_bounds__(256) gen_normals_kernel(float* z, const DeviceCounters* cnt, unsigned long long seed, int count, int ahead, int uniform) {
     const unsigned long long iter = cnt->iteration + (unsigned long long)ahead;
     float* dst = z + (iter & 1) * (long long)count;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x)
-        dst[e] = (float)stream_normal(seed, iter, STREAM_PROPOSAL, (unsigned long long)e);
+        dst[e] = (float)stream_step(seed, iter, (unsigned long long)e, uniform);
 }
 
 // proposal_value with the normals read from a prefetched table instead of being generated in place

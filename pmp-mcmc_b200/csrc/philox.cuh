@@ -9,6 +9,7 @@
 // approximations with a hand-rolled log for the tails.  tests/ checks it against an independent C restatement.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 namespace pmp {
 
@@ -146,6 +147,12 @@ __host__ __device__ __forceinline__ double det_norm_ppf(double u) {
 // Standard normal number `idx` of (seed, iter, stream), binary64.
 __host__ __device__ __forceinline__ double stream_normal(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx) {
     return det_norm_ppf(u64_to_open(stream_u64(seed, iter, stream, idx)));
+}
+
+// Proposal increment number `idx`: a standard normal, or 2u-1 (uniform on [-1,1)) for PMP_FLAG_UNIFORM_PROPOSAL.
+__host__ __device__ __forceinline__ double stream_step(uint64_t seed, uint64_t iter, uint64_t idx, int uniform) {
+    if (uniform) return PMP_FMA(2.0, u64_to_unit(stream_u64(seed, iter, STREAM_PROPOSAL, idx)), -1.0);
+    return stream_normal(seed, iter, STREAM_PROPOSAL, idx);
 }
 
 }  // namespace pmp

@@ -74,7 +74,7 @@ static void drop_graph(pmp_ctx* c) {
 
 // ---- launches ------------------------------------------------------------------------------------------------
 static int launch_propose(pmp_ctx* c) {
-    ProposeArgs a{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha};
+    ProposeArgs a{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0};
     long long total = (long long)c->P * c->cfg.dim;
     long long blocks = (total + 255) / 256;
     long long cap = (long long)c->sm_count * 8;
@@ -116,7 +116,7 @@ static int launch_sweep_linear(pmp_ctx* c, int generate) {
     if (gx > want) gx = want;
     if (gx < 1) gx = 1;
     SweepArgs a{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, TP, TD, sat_limit(c), generate, c->d_z,
-                ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha},
+                ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0},
                 c->d_dbg};
     if (env_int("PMP_SWEEP_SCALAR", 0)) sweep_linear_kernel<R, false><<<(unsigned)gx, SWEEP_THREADS, sweep_smem_bytes(), c->stream>>>(a);
     else sweep_linear_kernel<R, true><<<(unsigned)gx, SWEEP_THREADS, sweep_smem_bytes(), c->stream>>>(a);
@@ -155,7 +155,7 @@ static bool fast_accept_ok(const pmp_ctx* c) {
 
 static int launch_accept_fast(pmp_ctx* c, int make_next) {
     AcceptFastArgs fa{make_accept_args(c, 1, 0, 1, nullptr), c->d_z, make_next,
-                      ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha}};
+                      ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0}};
     size_t smem = (size_t)c->P * (c->cfg.algo == PMP_ALGO_PSP ? 4 : 2) * sizeof(double);
     switch (c->cfg.algo) {
         case PMP_ALGO_MP: accept_fast_kernel<PMP_ALGO_MP><<<1, ACCEPT_THREADS, smem, c->stream>>>(fa); break;
@@ -640,6 +640,21 @@ int pmp_run_timed(pmp_ctx* c, int64_t iters, float* total_ms, float* sweep_ms) {
     return PMP_OK;
 }
 
+int pmp_time_sweep(pmp_ctx* c, int reps, float* ms) {
+    PMP_REQUIRE(c && c->configured && ms && reps > 0, "bad arguments");
+    PMP_REQUIRE(c->cfg.target == PMP_TARGET_LINEAR_GAUSS, "pmp_time_sweep: linear-Gaussian target only");
+    PMP_CUDA(cudaSetDevice(c->device));
+    int rc;
+    for (int i = 0; i < 3; ++i) if ((rc = launch_sweep_linear(c, 0))) return rc;
+    PMP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) if ((rc = launch_sweep_linear(c, 0))) return rc;
+    PMP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PMP_CUDA(cudaMemsetAsync(c->d_acc, 0, c->P * sizeof(unsigned long long), c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    PMP_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return PMP_OK;
+}
+
 int pmp_launch_count(pmp_ctx* c, int64_t* launches) {
     PMP_REQUIRE(c && launches, "NULL argument");
     *launches = c->launches;
@@ -673,6 +688,18 @@ int pmp_debug_stamps(pmp_ctx* c, unsigned long long* out64) {
     PMP_REQUIRE(c && out64 && c->d_dbg, "debug stamps not enabled (PMP_DEBUG_STAMPS=1 before pmp_create)");
     PMP_CUDA(cudaStreamSynchronize(c->stream));
     PMP_CUDA(cudaMemcpy(out64, c->d_dbg, (64 + 3 * 1024) * 8, cudaMemcpyDeviceToHost));
+    return PMP_OK;
+}
+
+int pmp_stream_uniforms(uint64_t seed, uint64_t iteration, uint32_t stream, uint64_t idx0, int64_t count, double* out) {
+    PMP_REQUIRE(out && count >= 0, "bad arguments");
+    for (int64_t i = 0; i < count; ++i) out[i] = u64_to_unit(stream_u64(seed, iteration, stream, idx0 + (uint64_t)i));
+    return PMP_OK;
+}
+
+int pmp_stream_normals(uint64_t seed, uint64_t iteration, uint32_t stream, uint64_t idx0, int64_t count, double* out) {
+    PMP_REQUIRE(out && count >= 0, "bad arguments");
+    for (int64_t i = 0; i < count; ++i) out[i] = stream_normal(seed, iteration, stream, idx0 + (uint64_t)i);
     return PMP_OK;
 }
 

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) sweep_linear_kernel(const __
             const int per = (zcount + gridDim.x - 1) / gridDim.x;
             const int k = SWEEP_THREADS - 1 - tid, e = blockIdx.x * per + k;
             if (k < per && e < zcount)
-                a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_normal(a.gen.seed, iter + 1, STREAM_PROPOSAL, (unsigned long long)e);
+                a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
         }
         first_segment = false;
         // ---- segment flush, integer adds only: lanes that share a node (warp shuffles) → one row per warp in shared
