@@ -174,7 +174,7 @@ static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sw
         // fused chain loop: the acceptance kernel of iteration i publishes the nodes of iteration i+1 from the normals
         // table that the sweep of iteration i filled as a side job; only the first iteration of a run (or of a captured
         // graph, which cannot know what preceded it) builds its table and nodes with the stand-alone kernels.
-        const int fused = env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c) && c->world == 1;
+        const int fused = env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c);
         const bool chained = fused && !first_of_graph && c->z_valid_iter == (long long)c->host_iter;
         if (!chained && (rc = launch_propose(c))) return rc;
         if (sweep_begin) PMP_CUDA(cudaEventRecord(sweep_begin, c->stream));
@@ -591,7 +591,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
             PMP_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
             c->launches += c->graph_launches_total;
             c->host_iter += GI;
-            c->z_valid_iter = (env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c) && c->world == 1) ? (long long)c->host_iter : -1;
+            c->z_valid_iter = (env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c)) ? (long long)c->host_iter : -1;
         }
     }
     for (; done < iters; ++done) if ((rc = enqueue_iteration(c, nullptr, nullptr, false))) return rc;

@@ -1,0 +1,85 @@
+"""Worker for the multi-rank tests (launched by torch.distributed.run).  Backend nccl on GPUs, gloo on CPU (--cpu).
+GPU mode: runs the sharded device-resident chain and writes rank 0's trace; the parent compares it with a 1-GPU run.
+CPU mode: exercises the rendezvous / sharding host logic with a stand-in context (no kernels)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--points", dest="n", type=int, default=30000)
+    ap.add_argument("--iters", type=int, default=40)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as td
+    from conftest import synthetic_linear
+    from pmp_mcmc_b200 import _lib as L, dist as pdist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    x, y = synthetic_linear(a.n, seed=21)
+    if a.cpu:
+        td.init_process_group("gloo")
+        made = {}
+
+        class FakeContext:                      # records what create_context hands to the library
+            def __init__(self, device=0, world_size=1, rank=0, nccl_unique_id=None):
+                made.update(device=device, world_size=world_size, rank=rank, uid=bytes(nccl_unique_id))
+                self.world_size, self.rank = world_size, rank
+
+            @staticmethod
+            def nccl_unique_id():
+                return bytes(range(128))
+
+            def set_data_linear(self, xs, ys, n_offset=0, n_global=None):
+                made.update(lo=n_offset, n_local=len(xs), n_global=n_global, sx=float(np.sum(xs, dtype=np.float64)))
+
+        real = L.Context
+        L.Context = FakeContext
+        try:
+            ctx = pdist.create_context(device=0)
+            lo, hi = pdist.set_data_linear_sharded(ctx, x, y)
+        finally:
+            L.Context = real
+        assert made["uid"] == bytes(range(128)) and made["world_size"] == world and made["rank"] == rank
+        assert lo % 64 == 0 and made["n_global"] == a.n and made["n_local"] == hi - lo
+        t = torch.tensor([float(hi - lo), made["sx"]], dtype=torch.float64)
+        td.all_reduce(t)
+        assert int(t[0].item()) == a.n                                   # shards tile the dataset exactly
+        assert abs(t[1].item() - float(np.sum(x, dtype=np.float64))) < 1e-6
+        if rank == 0:
+            np.savez(a.out, ok=1, world=world)
+        td.destroy_process_group()
+        return
+    torch.cuda.set_device(local)
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pdist.create_context(local)
+    res = {}
+    for name, tree, b, depth, algo, draw, scale in (("mp", 0, 256, 1, L.ALGO_MP, L.DRAW_CUDA, 1000.0), ("psp", 1, 2, 6, L.ALGO_PSP, L.DRAW_PYTHON, 600.0)):
+        ctx.configure(tree, b=b, depth=depth, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=algo, draw=draw, alpha=0.02, scale=scale)
+        pdist.set_data_linear_sharded(ctx, x, y)
+        ctx.set_state([-0.8, 1.7, 0.7]); ctx.seed(99, 0)
+        ctx.trace_config(a.iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW)
+        ctx.run(a.iters)
+        tr = ctx.read_trace()
+        # every rank must hold the identical chain (replicated acceptance on identical reduced sums)
+        t = torch.from_numpy(tr["state"].copy()).cuda()
+        ref = t.clone(); td.broadcast(ref, src=0)
+        assert torch.equal(t, ref)
+        for k in ("state", "next", "draws", "logw"):
+            res[name + "_" + k] = tr[k]
+    if rank == 0:
+        np.savez(a.out, world=world, **res)
+    ctx.close()
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
