@@ -57,6 +57,7 @@ def lib():
         L.oracle_loglik_linear_suffstat.argtypes = [fp, fp, i64, fp, ctypes.c_int, dbl, dp]
         L.oracle_sumsq_fixed_mirror.argtypes = [fp, fp, i64, fp, ctypes.c_int, i64, ctypes.POINTER(u64)]
         L.oracle_blocked_cdf.argtypes = [dp, ctypes.c_int, dp]
+        L.oracle_set_chain.argtypes = [u64]
         _LIB = L
     return _LIB
 
@@ -103,11 +104,12 @@ def num_nodes(tree, b, depth):
     return b if tree == TREE_FLAT else (2 ** depth if tree == TREE_BINARY else b ** depth)
 
 
-def propose(tree, b, depth, dim, alpha, state, seed, it, uniform=False):
+def propose(tree, b, depth, dim, alpha, state, seed, it, uniform=False, chain=0):
     P = num_nodes(tree, b, depth)
     st = _f32(state)
     out = np.empty((P, dim), dtype=np.float32)
     lib().oracle_set_uniform_steps(1 if uniform else 0)
+    lib().oracle_set_chain(ctypes.c_uint64(chain))
     lib().oracle_propose(tree, b, depth, dim, ctypes.c_float(alpha), _fptr(st), seed, it, _fptr(out))
     return out
 
@@ -333,3 +335,116 @@ def log_banana(x):                       # banana_data.ipynb cell 2 L1-5 (log of
 def log_stdnormal(x):                    # com_dim.py:13-15 with mu=0, cov=I (log of)
     x = np.asarray(x, dtype=np.float64)
     return float(-0.5 * np.sum(x * x) - 0.5 * len(x) * math.log(2 * math.pi))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# analytic chains
+def analytic_logtarget(target, x, p0=0.0, p1=1.0):
+    """target: 1 normal1d (error.py:11-14), 2 banana (banana_data.ipynb cell 2), 3 N(0, I_d) (com_dim.py:13-15)."""
+    x = np.asarray(x, dtype=np.float64)
+    if target == 1:
+        return log_normal1d(float(x[0]), p0, p1)
+    if target == 2:
+        return log_banana(x)
+    return log_stdnormal(x)
+
+
+def logweights(algo, lt, props, b, depth, ks=1.0, use_kernel=True, quirk_level_mod=False, quirk_const=False):
+    """algo ids of include/pmp_b200.h: 2 MP, 3 PSP, 4 PMP, 5 TABLE."""
+    if algo == 2:
+        return mp_logweights(lt, props, ks, use_kernel)
+    if algo == 3:
+        return psp_logweights(lt, props, depth, ks, use_kernel)
+    if algo == 4:
+        return pmp_logweights(lt, props, b, depth, ks, use_kernel, quirk_level_mod)
+    if not use_kernel and not quirk_const:
+        return np.array(lt, dtype=np.float64)
+    return table_logweights(lt, props, b, depth, ks, quirk_const)
+
+
+def draw_sequential(w, u, side="right"):
+    """csrc/chains.cu: plain sequential cumsum (NumPy's association), unnormalised compare with u*total."""
+    cdf = np.cumsum(np.asarray(w, dtype=np.float64))
+    return np.minimum(cdf.searchsorted(np.asarray(u, dtype=np.float64) * cdf[-1], side=side), len(w) - 1).astype(np.int32)
+
+
+def analytic_chain(tree, b, depth, dim, target, algo, draw, alpha, seed, iters, state0, chain=0, scale=1.0, p0=0.0, p1=1.0,
+                   ks=1.0, use_kernel=True, quirk_level_mod=False, uniform=False, it0=0):
+    """One chain of csrc/chains.cu (and of pmp_run on an analytic target for chain=0), step by step.
+    algo 0 MH / 1 Barker need b=2 flat.  draw: 0 python rule, 1 cuda rule, 2 single."""
+    P = num_nodes(tree, b, depth)
+    bb = 2 if tree == TREE_BINARY else b
+    state = _f32(state0).copy()
+    base = chain << 32
+    samples = np.empty((iters, P, dim), dtype=np.float32)
+    states = np.empty((iters, dim), dtype=np.float32)
+    nexts = np.empty(iters, dtype=np.int32)
+    for k in range(iters):
+        it = it0 + k
+        props = propose(tree, b, depth, dim, alpha, state, seed, it, uniform, chain)
+        lt = np.array([analytic_logtarget(target, props[p], p0, p1) / scale for p in range(P)])
+        if algo in (0, 1):
+            u = stream_uniforms(seed, it, STREAM_DRAW, base, 1)[0]
+            if algo == 0:
+                nxt = int(u < math.exp(min(700.0, lt[1] - lt[0])))
+            else:
+                m = max(lt[0], lt[1]); w0, w1 = math.exp(lt[0] - m), math.exp(lt[1] - m)
+                nxt = int(w1 / (w0 + w1) > u)
+            d = np.full(P, nxt, dtype=np.int32)
+            d[0] = nxt
+        else:
+            A = logweights(algo, lt, props.astype(np.float64), bb, depth, ks, use_kernel, quirk_level_mod)
+            w = weights_from_log(A)
+            nd = 1 if draw == 2 else P
+            u = stream_uniforms(seed, it, STREAM_DRAW, base, nd)
+            dd = draw_sequential(w, u, "left" if draw == 1 else "right")
+            nxt = int(dd[pick_index(stream_uniforms(seed, it, STREAM_PICK, base, 1)[0], P)]) if draw == 0 else int(dd[0])
+            d = np.full(P, nxt, dtype=np.int32)
+            d[:nd] = dd
+        samples[k] = props[d]
+        state = props[nxt].copy()
+        states[k] = state
+        nexts[k] = nxt
+    return {"samples": samples, "states": states, "next": nexts}
+
+
+def error_py_replay(kind, hops, mu, sigma, N, deep, x0, normals, us, picks):
+    """simple_sampling/error/error.py MP (43-77), PSP (78-134), PMP (137-190) restated with the oracle's weight rules,
+    driven by recorded streams: `normals` in the order the script draws them, `us[h]` the P uniforms pandas' sample
+    consumed at hop h, `picks[h]` the index np.random.choice returned.  Returns the full X (before the burn-in cut)."""
+    b = N + 1
+    if kind == "MP":
+        P, tree, algo, depth = b, TREE_FLAT, 2, 1
+    elif kind == "PSP":
+        depth = int(math.log2(N + 1)); P, tree, algo = N + 1, TREE_BINARY, 3
+    else:
+        depth = deep; P, tree, algo = b ** deep, TREE_BARY, 4
+    nz = iter(normals)
+    X = np.empty(hops * P)
+    Y = np.empty(P)
+
+    def regenerate(root):
+        Y[0] = root
+        if kind == "MP":                                   # error.py:51-53 / 73-75
+            for i in range(N):
+                Y[i + 1] = root + next(nz)
+        elif kind == "PSP":                                # error.py:88-91 / 129-132
+            for i in range(depth):
+                j = 2 ** i
+                for k in range(j):
+                    Y[k + j] = Y[k] + next(nz)
+        else:                                              # error.py:145-149 / 184-188
+            for dee in range(deep):
+                temp = b ** dee
+                for j in range(N):
+                    for k in range(temp):
+                        Y[k + temp * (j + 1)] = Y[k] + next(nz)
+
+    regenerate(x0)
+    for h in range(hops):
+        lt = np.array([log_normal1d(Y[p], mu, sigma) for p in range(P)])
+        A = logweights(algo, lt, Y.reshape(-1, 1), 2 if kind == "PSP" else b, depth, 1.0, True, quirk_level_mod=True)
+        d = draw_numpy(weights_from_log(A), us[h])
+        X[h * P:(h + 1) * P] = Y[d]
+        regenerate(X[h * P + picks[h]])
+    return X

@@ -114,9 +114,12 @@ void oracle_stream_uniforms(uint64_t seed, uint64_t iter, uint32_t stream, uint6
  *    tree 2: (N+1)-ary   conv_pmp.cu:182-197, lb.py:356-360, error.py:145-149 */
 static float step32(float parent, float alpha, double z) { volatile float inc = alpha * (float)z; return parent + inc; }
 
+static uint64_t g_chain = 0;       /* chain id: upper 32 bits of the element index (csrc/chains.cu) */
+void oracle_set_chain(uint64_t chain) { g_chain = chain; }
 static int g_uniform_steps = 0;   /* 1: increments alpha*(2u-1) — random.uniform(-alpha, alpha), error.py:27 */
 void oracle_set_uniform_steps(int on) { g_uniform_steps = on; }
 static double step_value(uint64_t seed, uint64_t iter, uint64_t idx) {
+    idx |= g_chain << 32;
     if (g_uniform_steps) return fma(2.0, oracle_u64_to_unit(oracle_stream_u64(seed, iter, 0, idx)), -1.0);
     return oracle_stream_normal(seed, iter, 0, idx);
 }

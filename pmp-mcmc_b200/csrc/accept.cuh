@@ -34,7 +34,7 @@ struct ProposeArgs {
 // One thread per (node, coordinate).  The value is built along the node's ancestor chain in float32 with the
 // reference's two roundings per step: child = fl(parent + fl(alpha * z))  (normal_distribution<float>(0, alpha),
 // torch.normal(0, alpha)).  z for the step that created node `a` is normal number a*dim + j of the iteration.
-__device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long long iter, int node, int j, float v) {
+static __device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long long iter, int node, int j, float v) {
     if (a.tree == PMP_TREE_FLAT) {
         if (node > 0) {
             float z = (float)stream_step(a.seed, iter, (unsigned long long)node * a.dim + j, a.uniform);
@@ -56,7 +56,7 @@ __device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long
     return v;
 }
 
-__global__ void __launch_bounds__(256) propose_kernel(ProposeArgs a) {
+static __global__ void __launch_bounds__(256) propose_kernel(ProposeArgs a) {
     const unsigned long long iter = a.cnt->iteration;
     long long total = (long long)a.P * a.dim;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
@@ -420,15 +420,6 @@ template <int ALGO>
 __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(const __grid_constant__ AcceptArgs a) {
     extern __shared__ double accept_sm[];
     accept_device<ALGO>(a, accept_sm);
-}
-
-// Standard normals of one iteration as float32: z[(iter & 1) * P*dim + node*dim + j].  The fused sweep fills the other
-// half for iteration+1 while it runs (they depend on counters only, never on the chain state).
-__global__ void __launch_bounds__(256) gen_normals_kernel(float* z, const DeviceCounters* cnt, unsigned long long seed, int count, int ahead, int uniform) {
-    const unsigned long long iter = cnt->iteration + (unsigned long long)ahead;
-    float* dst = z + (iter & 1) * (long long)count;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x)
-        dst[e] = (float)stream_step(seed, iter, (unsigned long long)e, uniform);
 }
 
 // proposal_value with the normals read from a prefetched table instead of being generated in place

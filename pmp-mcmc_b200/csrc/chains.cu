@@ -1,9 +1,296 @@
-// chains.cu — batched independent chains on analytic targets.  Placeholder; filled in next.
+// chains.cu — batched independent chains on the analytic targets.
+//
+// Replaces the hop loops of simple_sampling/error/error.py (SP 17-40, MP 43-77, PSP 78-134, PMP 137-190), of
+// complex_nets/correlation/com_dim.py (PMP 24-86) and the banana density of banana_data.ipynb cell 2.  Those targets have
+// no data, so one chain is a few hundred flops per hop and a GPU is only useful on many chains at once: one THREAD per
+// chain, state and tree nodes in chain-fastest layouts ([dim][n_chains], [P][dim][n_chains]) so that every load and store
+// of a warp is one coalesced 128-byte line.  With sample recording on, the kernel is bound by the HBM write of the
+// resampled points (4*dim bytes per node evaluation); everything else stays in L1/L2-backed scratch.
+// Per chain and hop: Philox increments (chain id in the upper 32 bits of the element index) → tree nodes in float32 →
+// log-target in binary64 → MP / binary-Barker / general-tree weights → sequential cdf (the association NumPy's cumsum
+// uses) → P inverse-CDF draws and the pick of the next state.  Chain 0 uses the same stream elements as pmp_run.
+#include "accept.cuh"
 #include "common.cuh"
-extern "C" {
-int pmp_chains_create(pmp_ctx*, int64_t, const float*) { pmp::set_error("chains not built yet"); return PMP_ERR_UNSUPPORTED; }
-int pmp_chains_run(pmp_ctx*, int64_t, int) { pmp::set_error("chains not built yet"); return PMP_ERR_UNSUPPORTED; }
-int pmp_chains_read_states(pmp_ctx*, float*) { pmp::set_error("chains not built yet"); return PMP_ERR_UNSUPPORTED; }
-int pmp_chains_read_samples(pmp_ctx*, float*, int64_t) { pmp::set_error("chains not built yet"); return PMP_ERR_UNSUPPORTED; }
-int pmp_chains_run_timed(pmp_ctx*, int64_t, int, float*) { pmp::set_error("chains not built yet"); return PMP_ERR_UNSUPPORTED; }
+#include "philox.cuh"
+
+namespace pmp {
+
+struct ChainArgs {
+    pmp_config cfg;
+    int P;
+    long long n_chains;
+    float* states;            // [dim][n_chains]
+    float* nodes;             // [P][dim][n_chains] scratch
+    double* work;             // [3][P][n_chains] scratch: lt, A/cdf, level scratch
+    int* draws;               // [P][n_chains] scratch
+    float* samples;           // [iters][P][dim][n_chains] or nullptr
+    unsigned long long seed, iter0;
+    int iters;
+};
+
+__device__ __forceinline__ double chain_log_kernel(const float* nodes, long long nc, int dim, int a, int b, long long c, double ks, double lnk) {
+    double s = 0.0;
+    for (int j = 0; j < dim; ++j) {
+        double d = (double)nodes[((long long)a * dim + j) * nc + c] - (double)nodes[((long long)b * dim + j) * nc + c];
+        s = fma(d, d, s);
+    }
+    return dim * lnk - 0.5 * s / (ks * ks);
 }
+
+__global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    const pmp_config& cfg = a.cfg;
+    const int P = a.P, dim = cfg.dim;
+    const long long nc = a.n_chains;
+    const int b = (cfg.tree == PMP_TREE_BINARY) ? 2 : cfg.b;
+    const int D = (cfg.tree == PMP_TREE_FLAT) ? 1 : cfg.depth;
+    const double ks = (double)cfg.kernel_sigma;
+    const double lnk = -HALF_LOG_2PI - log(ks);
+    const bool use_kernel = !(cfg.flags & PMP_FLAG_NO_KERNEL_TERM);
+    const int uniform = (cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0;
+    const unsigned long long cbase = (unsigned long long)c << 32;
+    double* lt = a.work;
+    double* A = a.work + (long long)P * nc;
+    double* tmp = a.work + 2ll * P * nc;
+#define NODE(p, j) a.nodes[((long long)(p) * dim + (j)) * nc + c]
+#define W(arr, p) arr[(long long)(p) * nc + c]
+
+    for (int it = 0; it < a.iters; ++it) {
+        const unsigned long long iter = a.iter0 + (unsigned long long)it;
+        // ---- tree nodes (parents precede children in index order for all three shapes)
+        for (int j = 0; j < dim; ++j) NODE(0, j) = a.states[(long long)j * nc + c];
+        for (int p = 1; p < P; ++p) {
+            int parent = 0;
+            if (cfg.tree != PMP_TREE_FLAT) { long long s = 1; while ((long long)p >= s * b) s *= b; parent = (int)(p % s); }
+            for (int j = 0; j < dim; ++j) {
+                float z = (float)stream_step(a.seed, iter, cbase | (unsigned long long)((long long)p * dim + j), uniform);
+                NODE(p, j) = __fadd_rn(NODE(parent, j), __fmul_rn(cfg.alpha, z));
+            }
+        }
+        // ---- log-targets
+        for (int p = 0; p < P; ++p) W(lt, p) = analytic_logtarget(cfg.target, &NODE(p, 0), (int)nc, dim, cfg.target_p0, cfg.target_p1) / (double)cfg.scale;
+        // ---- log-weights
+        int next;
+        int n_draws = (cfg.draw == PMP_DRAW_SINGLE) ? 1 : P;
+        if (cfg.algo == PMP_ALGO_MH || cfg.algo == PMP_ALGO_BARKER) {
+            double u = u64_to_unit(stream_u64(a.seed, iter, STREAM_DRAW, cbase));
+            double l0 = W(lt, 0), l1 = W(lt, 1);
+            if (cfg.algo == PMP_ALGO_MH) next = u < exp((double)cfg.mh_temperature * (l1 - l0));
+            else { double m = fmax(l0, l1); double w0 = exp(l0 - m), w1 = exp(l1 - m); next = (w1 / (w0 + w1)) > u; }
+            W(a.draws, 0) = next; n_draws = 1;
+            W(A, 0) = l0; W(A, 1) = l1;
+        } else {
+            if (cfg.algo == PMP_ALGO_MP) {
+                for (int j = 0; j < P; ++j) {
+                    double v = W(lt, j);
+                    if (use_kernel) for (int k = 0; k < P; ++k) if (k != j) v += chain_log_kernel(a.nodes, nc, dim, j, k, c, ks, lnk);
+                    W(A, j) = v;
+                }
+            } else if (cfg.algo == PMP_ALGO_PSP) {
+                for (int p = 0; p < P; ++p) {
+                    double s = 0.0;
+                    for (int l = 0; l < D; ++l) { int m = p & ((2 << l) - 1), q = m ^ (1 << l); s += logsigmoid(W(lt, m) - W(lt, q)); }
+                    W(A, p) = s;
+                }
+            } else if (cfg.algo == PMP_ALGO_PMP) {
+                for (int p = 0; p < P; ++p) W(A, p) = 0.0;
+                long long s = 1;
+                for (int i = 0; i < D; ++i) {
+                    for (long long h = 0; h < s; ++h) {
+                        double mx = -INFINITY;
+                        for (int j = 0; j < b; ++j) {
+                            int nj = (int)(h + j * s);
+                            double v = W(lt, nj);
+                            if (use_kernel) for (int k = 0; k < b; ++k) if (k != j) v += chain_log_kernel(a.nodes, nc, dim, nj, (int)(h + k * s), c, ks, lnk);
+                            W(tmp, nj) = v; mx = fmax(mx, v);
+                        }
+                        double se = 0.0;
+                        for (int j = 0; j < b; ++j) se += exp(W(tmp, h + j * s) - mx);
+                        double lse = mx + log(se);
+                        for (int j = 0; j < b; ++j) { int nj = (int)(h + j * s); W(A, nj) += (mx == -INFINITY) ? -INFINITY : W(tmp, nj) - lse; }
+                    }
+                    if (i < D - 1) {
+                        long long lo = s * b, hi = s * b * b;
+                        long long mod = (cfg.flags & PMP_FLAG_QUIRK_LEVEL_MOD) ? (long long)b * (i + 1) : lo;
+                        for (long long x = lo; x < hi; ++x) W(A, x) = W(A, x % mod);
+                    }
+                    s *= b;
+                }
+            } else {   // TABLE
+                for (int p = 0; p < P; ++p) {
+                    double v = W(lt, p);
+                    if (cfg.flags & PMP_FLAG_QUIRK_TABLE_CONST) v += (double)D * (b - 1) * dim * (-HALF_LOG_2PI);
+                    else if (use_kernel) {
+                        long long s = 1;
+                        for (int d = 0; d < D; ++d) {
+                            long long m = p % (s * b), h = m % s;
+                            for (int k = 0; k < b; ++k) { long long o = h + k * s; if (o != m) v += chain_log_kernel(a.nodes, nc, dim, (int)m, (int)o, c, ks, lnk); }
+                            s *= b;
+                        }
+                    }
+                    W(A, p) = v;
+                }
+            }
+            if (cfg.flags & PMP_FLAG_STANDARDIZE) {
+                double mean = 0.0; for (int p = 0; p < P; ++p) mean += W(A, p); mean /= P;
+                double var = 0.0; for (int p = 0; p < P; ++p) { double d = W(A, p) - mean; var = fma(d, d, var); }
+                double sd = sqrt(var / (P - 1));
+                for (int p = 0; p < P; ++p) W(A, p) = (W(A, p) - mean) / sd;
+            }
+            // ---- sequential cdf and draws
+            double mx = -INFINITY;
+            for (int p = 0; p < P; ++p) mx = fmax(mx, W(A, p));
+            double run = 0.0;
+            for (int p = 0; p < P; ++p) { double w = exp(W(A, p) - mx); run += (w == w) ? w : 0.0; W(A, p) = run; }
+            const double total = run;
+            const bool right = (cfg.draw != PMP_DRAW_CUDA);
+            for (int t = 0; t < n_draws; ++t) {
+                double thr = u64_to_unit(stream_u64(a.seed, iter, STREAM_DRAW, cbase | (unsigned long long)t)) * total;
+                int lo = 0, hi = P;
+                while (lo < hi) { int mid = (lo + hi) >> 1; double v = W(A, mid); bool go = right ? (v <= thr) : (v < thr); if (go) lo = mid + 1; else hi = mid; }
+                W(a.draws, t) = min(lo, P - 1);
+            }
+            if (cfg.draw == PMP_DRAW_PYTHON) {
+                double up = u64_to_unit(stream_u64(a.seed, iter, STREAM_PICK, cbase));
+                next = W(a.draws, min(P - 1, (int)(up * (double)P)));
+            } else next = W(a.draws, 0);
+        }
+        // ---- record the resampled points (chain-fastest: coalesced 4-byte stores across the warp), new state
+        if (a.samples) {
+            float* out = a.samples + (long long)it * P * dim * nc;
+            for (int t = 0; t < P; ++t) {
+                int src = t < n_draws ? W(a.draws, t) : next;
+                for (int j = 0; j < dim; ++j) out[((long long)t * dim + j) * nc + c] = NODE(src, j);
+            }
+        }
+        for (int j = 0; j < dim; ++j) a.states[(long long)j * nc + c] = NODE(next, j);
+    }
+#undef NODE
+#undef W
+}
+
+__global__ void chains_transpose_in(const float* host_layout, float* states, long long n_chains, int dim) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_chains * dim) { long long c = i / dim; int j = (int)(i - c * dim); states[(long long)j * n_chains + c] = host_layout[i]; }
+}
+__global__ void chains_transpose_out(const float* states, float* host_layout, long long n_chains, int dim) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_chains * dim) { long long c = i / dim; int j = (int)(i - c * dim); host_layout[i] = states[(long long)j * n_chains + c]; }
+}
+
+struct ChainScratch { float* nodes = nullptr; double* work = nullptr; int* draws = nullptr; float* stage = nullptr; long long n_chains = 0; int P = 0, dim = 0; };
+
+}  // namespace pmp
+
+using namespace pmp;
+
+static ChainScratch* scratch_of(pmp_ctx* c) { return reinterpret_cast<ChainScratch*>(c->chain_scratch); }
+
+extern "C" {
+
+int pmp_chains_destroy(pmp_ctx* c) {
+    ChainScratch* s = scratch_of(c);
+    if (s) { cudaFree(s->nodes); cudaFree(s->work); cudaFree(s->draws); cudaFree(s->stage); delete s; c->chain_scratch = nullptr; }
+    if (c->d_chain_states) { cudaFree(c->d_chain_states); c->d_chain_states = nullptr; }
+    if (c->d_chain_samples) { cudaFree(c->d_chain_samples); c->d_chain_samples = nullptr; c->chain_samples_cap = 0; }
+    c->n_chains = 0;
+    return PMP_OK;
+}
+
+int pmp_chains_create(pmp_ctx* c, int64_t n_chains, const float* init_states) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_REQUIRE(n_chains >= 1, "n_chains must be >= 1");
+    PMP_REQUIRE(c->cfg.target == PMP_TARGET_NORMAL1D || c->cfg.target == PMP_TARGET_BANANA || c->cfg.target == PMP_TARGET_STDNORMAL,
+                "batched chains run the analytic targets only");
+    PMP_CUDA(cudaSetDevice(c->device));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    pmp_chains_destroy(c);
+    const int P = c->P, dim = c->cfg.dim;
+    ChainScratch* s = new ChainScratch();
+    c->chain_scratch = s;
+    s->n_chains = n_chains; s->P = P; s->dim = dim;
+    PMP_CUDA(cudaMalloc((void**)&c->d_chain_states, (size_t)n_chains * dim * sizeof(float)));
+    PMP_CUDA(cudaMalloc((void**)&s->nodes, (size_t)n_chains * P * dim * sizeof(float)));
+    PMP_CUDA(cudaMalloc((void**)&s->work, (size_t)n_chains * P * 3 * sizeof(double)));
+    PMP_CUDA(cudaMalloc((void**)&s->draws, (size_t)n_chains * P * sizeof(int)));
+    PMP_CUDA(cudaMalloc((void**)&s->stage, (size_t)n_chains * dim * sizeof(float)));
+    if (init_states) {
+        PMP_CUDA(cudaMemcpyAsync(s->stage, init_states, (size_t)n_chains * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        long long tot = n_chains * dim;
+        chains_transpose_in<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(s->stage, c->d_chain_states, n_chains, dim);
+        c->launches++;
+    } else PMP_CUDA(cudaMemsetAsync(c->d_chain_states, 0, (size_t)n_chains * dim * sizeof(float), c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_chains = n_chains;
+    c->chain_iteration = 0;
+    c->chain_iters_recorded = 0;
+    return PMP_OK;
+}
+
+static int chains_launch(pmp_ctx* c, int64_t iters, int record) {
+    PMP_REQUIRE(c && c->n_chains > 0 && scratch_of(c), "pmp_chains_create first");
+    PMP_REQUIRE(iters >= 0 && iters < (1ll << 31), "bad iters");
+    ChainScratch* s = scratch_of(c);
+    PMP_REQUIRE(s->P == c->P && s->dim == c->cfg.dim, "configuration changed since pmp_chains_create");
+    PMP_CUDA(cudaSetDevice(c->device));
+    if (record) {
+        long long need = (long long)iters * c->P * c->cfg.dim * c->n_chains;
+        if (need > c->chain_samples_cap) {
+            if (c->d_chain_samples) cudaFree(c->d_chain_samples);
+            c->d_chain_samples = nullptr; c->chain_samples_cap = 0;
+            cudaError_t e = cudaMalloc((void**)&c->d_chain_samples, (size_t)need * sizeof(float));
+            if (e != cudaSuccess) { set_error("cudaMalloc(%lld sample floats) failed: %s", need, cudaGetErrorString(e)); return PMP_ERR_ALLOC; }
+            c->chain_samples_cap = need;
+        }
+    }
+    ChainArgs a{c->cfg, c->P, c->n_chains, c->d_chain_states, s->nodes, s->work, s->draws, record ? c->d_chain_samples : nullptr,
+                c->seed, c->chain_iteration, (int)iters};
+    chains_kernel<<<(unsigned)((c->n_chains + 127) / 128), 128, 0, c->stream>>>(a);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    c->chain_iteration += (unsigned long long)iters;
+    c->chain_iters_recorded = record ? iters : 0;
+    return PMP_OK;
+}
+
+int pmp_chains_run(pmp_ctx* c, int64_t iters, int record_samples) {
+    int rc = chains_launch(c, iters, record_samples);
+    if (rc) return rc;
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_chains_run_timed(pmp_ctx* c, int64_t iters, int record_samples, float* total_ms) {
+    PMP_REQUIRE(c && total_ms, "NULL argument");
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    PMP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int rc = chains_launch(c, iters, record_samples);
+    if (rc) return rc;
+    PMP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    PMP_CUDA(cudaEventElapsedTime(total_ms, c->ev0, c->ev1));
+    return PMP_OK;
+}
+
+int pmp_chains_read_states(pmp_ctx* c, float* out) {
+    PMP_REQUIRE(c && out && c->n_chains > 0 && scratch_of(c), "pmp_chains_create first");
+    ChainScratch* s = scratch_of(c);
+    long long tot = c->n_chains * c->cfg.dim;
+    chains_transpose_out<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->d_chain_states, s->stage, c->n_chains, c->cfg.dim);
+    c->launches++;
+    PMP_CUDA(cudaMemcpyAsync(out, s->stage, (size_t)tot * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_chains_read_samples(pmp_ctx* c, float* out, int64_t count) {
+    PMP_REQUIRE(c && out && c->d_chain_samples, "no samples recorded");
+    long long have = c->chain_iters_recorded * c->P * c->cfg.dim * c->n_chains;
+    PMP_REQUIRE(count == have, "count %lld != recorded %lld", (long long)count, have);
+    PMP_CUDA(cudaMemcpyAsync(out, c->d_chain_samples, (size_t)have * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+}  // extern "C"

@@ -110,6 +110,7 @@ struct pmp_ctx {
     long long chain_samples_cap = 0;   // in floats
     long long chain_iters_recorded = 0;
     unsigned long long chain_iteration = 0;
+    void* chain_scratch = nullptr;
 
     // FC model
     void* fc = nullptr;

@@ -267,7 +267,8 @@ int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* 
     return PMP_OK;
 }
 
-int pmp_fc_destroy(pmp_ctx* ctx);   // fc_sweep.cu
+int pmp_fc_destroy(pmp_ctx* ctx);       // fc_sweep.cu
+int pmp_chains_destroy(pmp_ctx* ctx);   // chains.cu
 
 int pmp_destroy(pmp_ctx* c) {
     if (!c) return PMP_OK;
@@ -275,10 +276,10 @@ int pmp_destroy(pmp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     drop_graph(c);
     pmp_fc_destroy(c);
+    pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
-                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush,
-                    c->d_chain_states, c->d_chain_samples, c->d_z, c->d_done};
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
