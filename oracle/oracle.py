@@ -448,3 +448,52 @@ def error_py_replay(kind, hops, mu, sigma, N, deep, x0, normals, us, picks):
         X[h * P:(h + 1) * P] = Y[d]
         regenerate(X[h * P + picks[h]])
     return X
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FC model (complex_nets/Mnist/FC/PMP_FC.py:21-44): 784-512-256-128-10 ReLU MLP, loss = CrossEntropy(mean) / 10
+FC_SHAPES = [(512, 784), (512,), (256, 512), (256,), (128, 256), (128,), (10, 128), (10,)]   # torch parameter order
+FC_DIM = sum(int(np.prod(s)) for s in FC_SHAPES)
+
+
+def fc_unpack(theta):
+    out, off = [], 0
+    for s in FC_SHAPES:
+        k = int(np.prod(s))
+        out.append(np.asarray(theta[off:off + k]).reshape(s))
+        off += k
+    return out
+
+
+def fc_init_theta(seed=0):
+    """nn.Linear's default init (uniform +-1/sqrt(fan_in)) from a seeded generator: a deterministic stand-in for FC_model.pkl."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for s in FC_SHAPES:
+        fan_in = s[1] if len(s) == 2 else {512: 784, 256: 512, 128: 256, 10: 128}[s[0]]
+        parts.append(rng.uniform(-1, 1, size=int(np.prod(s))) / math.sqrt(fan_in))
+    return np.concatenate(parts).astype(np.float32)
+
+
+def fc_mean_ce_f64(X, y, theta):
+    """Ground truth: the forward pass of PMP_FC.py:30-36 and CrossEntropyLoss(mean) in binary64 from the float32 inputs."""
+    W1, b1, W2, b2, W3, b3, W4, b4 = [a.astype(np.float64) for a in fc_unpack(theta)]
+    h = np.maximum(np.asarray(X, dtype=np.float64).reshape(len(y), -1) @ W1.T + b1, 0)
+    h = np.maximum(h @ W2.T + b2, 0)
+    h = np.maximum(h @ W3.T + b3, 0)
+    z = h @ W4.T + b4
+    m = z.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(z - m).sum(axis=1))
+    return float(np.mean(lse - z[np.arange(len(y)), np.asarray(y)]))
+
+
+def fc_loss_torch32(X, y, theta, div=10.0):
+    """loss(net) exactly as the reference evaluates it (PMP_FC.py:40-44): torch float32, CrossEntropyLoss()(net(X), y) / 10."""
+    import torch
+    import torch.nn.functional as F
+    W1, b1, W2, b2, W3, b3, W4, b4 = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)) for a in fc_unpack(theta)]
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).view(-1, 28 * 28)
+        x = F.relu(F.linear(x, W1, b1)); x = F.relu(F.linear(x, W2, b2)); x = F.relu(F.linear(x, W3, b3))
+        x = F.linear(x, W4, b4)
+        return float(torch.nn.CrossEntropyLoss()(x, torch.from_numpy(np.asarray(y, dtype=np.int64))) / div)

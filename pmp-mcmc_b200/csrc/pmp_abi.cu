@@ -340,7 +340,7 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     if ((rc = dev_alloc(&c->d_logw, (size_t)P))) return rc;
     if ((rc = dev_alloc(&c->d_draws, (size_t)P))) return rc;
     if ((rc = dev_alloc(&c->d_uniforms, (size_t)P + 1))) return rc;
-    if ((rc = dev_alloc(&c->d_z, (size_t)2 * P * cfg->dim))) return rc;
+    if ((rc = dev_alloc(&c->d_z, cfg->target == PMP_TARGET_LINEAR_GAUSS ? (size_t)2 * P * cfg->dim : 0))) return rc;
     c->z_valid_iter = -1;
     PMP_CUDA(cudaMemset(c->d_acc, 0, P * sizeof(unsigned long long)));
     PMP_CUDA(cudaMemset(c->d_props, 0, (size_t)P * cfg->dim * sizeof(float)));
@@ -443,6 +443,13 @@ int pmp_write_proposals(pmp_ctx* c, const float* in, int64_t count) {
 }
 
 int pmp_fc_loglik(pmp_ctx* c);   // fc_sweep.cu: fills d_lt for PMP_TARGET_FC
+
+// internal (not in the public header): exact cross-rank sum of fixed-point partials on the ctx stream
+int pmp_allreduce_u64(pmp_ctx* c, unsigned long long* buf, size_t count) {
+    if (c->world <= 1) return PMP_OK;
+    PMP_NCCL(g_nccl.AllReduce(buf, buf, count, ncclUint64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+    return PMP_OK;
+}
 
 int pmp_loglik(pmp_ctx* c, double* out_host) {
     PMP_REQUIRE(c && c->configured, "ctx not configured");
