@@ -78,7 +78,7 @@ def load_fc(kind, X, y, device="cpu"):
         lines = f.readlines()
     ns = {"torch": torch, "F": F, "nn": nn, "copy": copy, "math": math, "np": np, "tqdm": lambda it: it, "device": device,
           "X": X, "y": y, "x_test": X[:16], "y_test": y[:16], "batch_size": int(X.shape[0]), "N": 7, "alpha": 1e-4}
-    ranges = {"PMP": [(20, 44), (77, 186)], "MP": [(20, 36), (68, 74), (76, 158)], "MH": [(15, 31), (66, 136)]}[kind]
+    ranges = {"PMP": [(20, 44), (77, 186)], "MP": [(20, 36), (69, 74), (76, 164)], "MH": [(17, 34), (66, 71), (72, 135)]}[kind]
     src = ""
     for a, b in ranges:
         src += "".join(lines[a:b]) + "\n"

@@ -36,3 +36,66 @@ def test_fc_logtarget_parity(ctx, n, P, alpha):
     ref32 = np.array([-o.fc_loss_torch32(X, y, props[p]) for p in range(min(P, 3))])
     np.testing.assert_allclose(lt[: len(ref32)], ref32, rtol=2e-5)
     assert np.array_equal(lt, ctx.loglik())          # integer-exact NLL sums: bitwise repeatable
+
+
+def _golden():
+    import os
+    from conftest import ROOT
+    from oracle import oracle as o
+    G = np.load(os.path.join(ROOT, "tests", "golden", "fc_step.npz"))
+    n = int(G["n"])
+    rng = np.random.default_rng(int(G["data_seed"]))
+    X = rng.standard_normal((n, 28, 28)).astype(np.float32)
+    y = rng.integers(0, 10, size=n).astype(np.int64)
+    return G, X, y, o.fc_init_theta(int(G["theta_seed"]))
+
+
+@pytest.mark.parametrize("kind", ["PMP", "MP"])
+def test_fc_step_against_reference_golden(ctx, kind):
+    """Reference PMPOptimizer.step / MPOptimizer.step (PMP_FC.py:105-143, MP_FC.py:102-122) on synthetic MNIST-shaped data."""
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    G, X, y, theta0 = _golden()
+    if kind == "PMP":
+        ctx.configure(L.TREE_BINARY, depth=3, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=float(G["alpha"]), scale=10.0)
+    else:
+        ctx.configure(L.TREE_FLAT, b=8, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_MP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE | L.FLAG_KERNEL_MEAN, alpha=float(G["alpha"]), scale=10.0)
+    ctx.set_data_fc(X.reshape(len(y), -1), y)
+    ctx.set_state(theta0); ctx.seed(int(G["prop_seed"]), 0); ctx.propose()
+    props = ctx.read_proposals()
+    lt = ctx.loglik()
+    np.testing.assert_allclose(-lt, G[kind + "_loss"], rtol=2e-5)                               # loss(net) of the reference, float32
+    truth = np.array([o.fc_mean_ce_f64(X, y, props[p]) / 10.0 for p in range(8)])
+    idx, nxt = ctx.accept(np.array([float(G[kind + "_u"])]))
+    A_dev = ctx.read_logweights()
+    if kind == "PMP":
+        A_true = o.standardize(o.psp_logweights(-truth, props[:, :4].astype(np.float64), 3, use_kernel=False))
+    else:
+        kt = o.mp_logweights(np.zeros(8), props.astype(np.float64) / np.sqrt(o.FC_DIM)) / 8.0     # sum_k mean_dim logK / P up to a constant
+        A_true = o.standardize(-truth + (kt - kt.mean()))
+    # standardisation blows differences of ~1e-6 up to O(1): the device (bf16x3) must track the binary64 weights; the reference's
+    # own float32 B is the noisier of the two (corr with the truth is checked in tests/test_cpu_fc.py)
+    assert np.max(np.abs(A_dev - A_true)) < 0.35, (A_dev, A_true)
+    assert np.corrcoef(A_dev, A_true)[0, 1] > 0.98
+    assert idx[0] == o.draw_blocked(o.weights_from_log(A_dev), [float(G[kind + "_u"])], "right")[0] == nxt
+    assert np.array_equal(ctx.get_state(), props[nxt])
+
+
+def test_fc_host_layer(ctx):
+    """fc.py: Model / loss / PMPOptimizer / MPOptimizer / MetropolisOptimizer with the reference's call pattern."""
+    import torch
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import fc
+    G, X, y, theta0 = _golden()
+    fc.set_data(X, y, ctx=ctx)
+    net = fc.unflatten(theta0)
+    assert isinstance(net, fc.Model) and np.array_equal(fc.flatten(net), theta0)
+    np.testing.assert_allclose(float(fc.loss(net)), G["PMP_loss"][0], rtol=2e-5)
+    props = o.propose(o.TREE_BINARY, 2, 3, o.FC_DIM, float(G["alpha"]), theta0, int(G["prop_seed"]), 0)
+    nets = [fc.unflatten(props[i]) for i in range(8)]
+    opt = fc.PMPOptimizer(fc.unflatten(theta0), alpha=1e-4)
+    opt.step(1, nets, [torch.from_numpy(p) for p in props], torch.tensor(o.FC_DIM), uniforms=np.array([float(G["PMP_u"])]))
+    assert any(opt.net is n for n in nets) and abs(opt.loss - 2.31017) < 1e-3
+    for cls in (fc.PMPOptimizer, fc.MPOptimizer, fc.MetropolisOptimizer):
+        tr = cls(fc.unflatten(theta0), alpha=1e-4, seed=4).fit(num_steps=3)
+        assert tr.shape == (3,) and np.all(np.abs(tr - 2.3102) < 2e-3)
