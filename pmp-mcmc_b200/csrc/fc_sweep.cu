@@ -109,7 +109,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) fc_gemm_kernel(const __grid_c
     __shared__ float s_red[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y, batch = blockIdx.z;
+    // rasterisation: (n-block, node) fastest, so the CTAs that share an A tile (the data rows) run together and the tile is
+    // read from HBM once and then from L2; the per-node weights (a few MB) stay L2-resident across the whole launch
+    const int nblk_n = g.n_total / BN;
+    const int m_blk = blockIdx.y, n_blk = blockIdx.x % nblk_n, batch = blockIdx.x / nblk_n;
     const int num_k = g.K3 / BK;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 
@@ -333,7 +336,7 @@ template <int BN, int EPI>
 static int launch_gemm(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int n_total, int nb) {
     static bool attr = false;
     if (!attr) { PMP_CUDA(cudaFuncSetAttribute(fc_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN, EPI>())); attr = true; }
-    dim3 grid((g.M + BM - 1) / BM, n_total / BN, nb);
+    dim3 grid((n_total / BN) * nb, (g.M + BM - 1) / BM, 1);
     fc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, gemm_smem<BN, EPI>(), c->stream>>>(a, b, g);
     c->launches++;
     PMP_CUDA(cudaGetLastError());
