@@ -425,14 +425,14 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_kernel(const __grid_
 // proposal_value with the normals read from a prefetched table instead of being generated in place
 __device__ __forceinline__ float proposal_value_z(const ProposeArgs& a, const float* __restrict__ z, int node, int j, float v) {
     if (a.tree == PMP_TREE_FLAT) {
-        if (node > 0) v = __fadd_rn(v, __fmul_rn(a.alpha, z[(long long)node * a.dim + j]));
+        if (node > 0) v = __fadd_rn(v, __fmul_rn(a.alpha, __ldcg(z + (long long)node * a.dim + j)));   // L2 loads: the table is written by other SMs
         return v;
     }
     const int b = (a.tree == PMP_TREE_BINARY) ? 2 : a.b;
     long long s = 1;
     for (int l = 0; l < a.depth; ++l) {
         long long digit = (node / s) % b;
-        if (digit != 0) { long long anc = node % (s * b); v = __fadd_rn(v, __fmul_rn(a.alpha, z[anc * a.dim + j])); }
+        if (digit != 0) { long long anc = node % (s * b); v = __fadd_rn(v, __fmul_rn(a.alpha, __ldcg(z + anc * a.dim + j))); }
         s *= b;
     }
     return v;

@@ -25,9 +25,8 @@ __device__ __forceinline__ double warp_sum_all(double v) { for (int o = 16; o > 
 __device__ __forceinline__ double warp_max_all(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 
 template <int ALGO>
-__global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_fast_kernel(const __grid_constant__ AcceptFastArgs fa) {
+__device__ __forceinline__ void accept_fast_body(const AcceptFastArgs& fa, double* sm) {
     const AcceptArgs& a = fa.base;
-    extern __shared__ double sm[];
     const int P = a.P;
     double* lt = sm;                     // [P]   log-targets; later reused as int32 draws
     double* A = sm + P;                  // [P]   log-weights → weights → cdf
@@ -41,8 +40,8 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_fast_kernel(const __
     PMP_STAMP(dbg, 0);
 
     // ---- phase 0: everything independent of the sweep -------------------------------------------------------------
-    const unsigned long long iter = a.cnt->iteration;
-    const long long row = a.cnt->trace_rows;
+    const unsigned long long iter = __ldcg(&a.cnt->iteration);      // L2 loads throughout: in the persistent kernel these change
+    const long long row = __ldcg(&a.cnt->trace_rows);               // between iterations of the same launch
     const float s0 = __ldcg(a.props), s1v = __ldcg(a.props + 1), s2v = __ldcg(a.props + 2);   // node 0 = current state
     const int n_draws = (cfg.draw == PMP_DRAW_SINGLE) ? 1 : P;
     const bool right = (cfg.draw != PMP_DRAW_CUDA);
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_fast_kernel(const __
     const bool rec = row < a.trace.capacity;
     if (rec) {
         if (a.trace.what & PMP_TRACE_DRAWS) for (int t = tid; t < P; t += ACCEPT_THREADS) a.trace.draws[row * P + t] = t < n_draws ? sdraw[t] : -1;
-        if (a.trace.what & PMP_TRACE_LOGW) for (int t = tid; t < P; t += ACCEPT_THREADS) a.trace.logw[row * P + t] = a.logw[t];
+        if (a.trace.what & PMP_TRACE_LOGW) for (int t = tid; t < P; t += ACCEPT_THREADS) a.trace.logw[row * P + t] = __ldcg(a.logw + t);
         if (a.trace.what & PMP_TRACE_SAMPLES)
             for (int g = tid; g < P * 3; g += ACCEPT_THREADS) { int t = g / 3, j = g - 3 * t; a.trace.samples[row * P * 3 + g] = __ldcg(a.props + 3 * (t < n_draws ? sdraw[t] : next) + j); }
     }
@@ -196,6 +195,12 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_fast_kernel(const __
         }
     }
     PMP_STAMP(dbg, 6);
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_fast_kernel(const __grid_constant__ AcceptFastArgs fa) {
+    extern __shared__ double accept_fast_sm[];
+    accept_fast_body<ALGO>(fa, accept_fast_sm);
 }
 
 }  // namespace pmp

@@ -1,0 +1,162 @@
+// chain_persistent.cuh — the whole device-resident chain as ONE cooperative kernel (single GPU, linear-Gaussian target).
+//
+// The stepwise loop (sweep kernel → acceptance kernel, replayed from a CUDA graph) pays per iteration for two launches,
+// for re-staging the same 0.8 MB of data into shared memory, for every CTA's prologue and for a cold instruction cache
+// in the one-CTA acceptance kernel.  None of that is work the algorithm asks for: the data never change, the node tile
+// of a CTA never changes, and the acceptance code is the same every iteration.  Here:
+//   * grid = one CTA of 1024 threads per SM (cooperative launch: co-residency is guaranteed or the launch fails);
+//   * CTAs 0..G-2 are sweep CTAs: each owns a fixed contiguous range of (128-node tile, 64-point chunk) units, stages
+//     its data slice into shared memory ONCE, and per iteration only re-reads its tile's nodes (1.5 KB), runs the
+//     packed-FMA inner loop and flushes integer partial sums (same arithmetic, same bits as sweep_linear_kernel);
+//   * CTA G-1 is the acceptance CTA: it waits for all sweep CTAs of the iteration, runs accept_fast_body (hot in its
+//     SM's instruction cache), publishes the next nodes and releases the next iteration;
+//   * the two hand-offs per iteration are release/acquire counters in global memory (bounded spins: a protocol bug
+//     traps instead of hanging the GPU).
+#pragma once
+#include "accept_fast.cuh"
+#include "sweep_linear.cuh"
+
+namespace pmp {
+
+constexpr int PERSIST_THREADS = 1024;
+constexpr int PERSIST_TP = 32, PERSIST_TD = PERSIST_THREADS / PERSIST_TP, PERSIST_R = 4, PERSIST_PT = PERSIST_TP * PERSIST_R;
+
+struct PersistSync {
+    unsigned int arrive;     // += 1 per sweep CTA per iteration
+    unsigned int version;    // iterations completed by the acceptance CTA in this launch
+};
+
+struct PersistArgs {
+    SweepArgs sw;            // x, y, theta (= props), acc, cnt, n_local, nchunks, P, ... (TP/TD fields unused)
+    AcceptFastArgs fa;
+    PersistSync* sync;
+    int iters;
+    int max_chunks;          // chunks per sweep CTA that fit the dynamic shared memory
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target) {
+    unsigned spins = 0;
+    while ((int)(ld_acquire(p) - target) < 0) { if (++spins > 400000000u) __trap(); }
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(const __grid_constant__ PersistArgs pa) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int tid = threadIdx.x;
+    const int n_sweep = gridDim.x - 1;
+
+    if ((int)blockIdx.x == n_sweep) {
+        // ================= acceptance CTA =================
+        for (int it = 0; it < pa.iters; ++it) {
+            if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 8] = clock64(); pa.fa.base.dbg[32 + 24] = globaltimer_ns(); }
+            if (tid == 0) spin_until_ge(&pa.sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
+            __syncthreads();
+            accept_fast_body<ALGO>(pa.fa, reinterpret_cast<double*>(dsm));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(&pa.sync->version, (unsigned)(it + 1));
+            if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 9] = clock64(); pa.fa.base.dbg[32 + 25] = globaltimer_ns(); }
+        }
+        return;
+    }
+
+    // ================= sweep CTAs =================
+    constexpr int R = PERSIST_R, TP = PERSIST_TP, TD = PERSIST_TD, PT = PERSIST_PT;
+    const SweepArgs& a = pa.sw;
+    float* tile = reinterpret_cast<float*>(dsm);                                           // [max_chunks][CHUNK_STRIDE]
+    unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE);   // [TD][PT]
+    __shared__ float sprops[PT * 3];
+    __shared__ double sscl[PT];
+
+    const int tp = tid & (TP - 1), td = tid / TP;
+    const int ntiles = (a.P + PT - 1) / PT;
+    const long long units = (long long)ntiles * a.nchunks;
+    const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
+    const int zcount = a.P * 3;
+
+    // ---- stage this CTA's data slice once: segment s covers chunks [c_begin, c_end) of node tile ptile -----------------
+    int nseg = 0; int seg_tile[3]; long long seg_c0[3], seg_c1[3]; int seg_slot[3];
+    {
+        long long u = u_begin; int slot = 0;
+        while (u < u_end && nseg < 3) {
+            int ptile = (int)(u / a.nchunks);
+            long long c0 = u - (long long)ptile * a.nchunks, c1 = min(a.nchunks, c0 + (u_end - u));
+            seg_tile[nseg] = ptile; seg_c0[nseg] = c0; seg_c1[nseg] = c1; seg_slot[nseg] = slot;
+            for (long long i = tid; i < (c1 - c0) * (CHUNK / 2); i += PERSIST_THREADS) {
+                int c = (int)(i / (CHUNK / 2)), k = (int)(i - (long long)c * (CHUNK / 2));
+                bool isy = k >= CHUNK / 4; int kk = isy ? k - CHUNK / 4 : k;
+                long long g = (c0 + c) * CHUNK + 4 * kk;
+                const float* src = (isy ? a.y : a.x) + (g < a.n_local ? g : 0);
+                cp_async16(tile + (size_t)(slot + c) * CHUNK_STRIDE + (isy ? CHUNK : 0) + 4 * kk, src, g < a.n_local ? 16 : 0);
+            }
+            slot += (int)(c1 - c0); u += c1 - c0; ++nseg;
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    bool saturated = false;
+    for (int it = 0; it < pa.iters; ++it) {
+        unsigned long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
+        PMP_STAMP(dbg, 0);
+        if (tid == 0 && it > 0) spin_until_ge(&pa.sync->version, (unsigned)it);
+        __syncthreads();
+        PMP_STAMP(dbg, 1);
+        if (a.generate) {   // side job of the last warps: this CTA's slice of the NEXT iteration's normals (every CTA, also one without units)
+            const unsigned long long iter = __ldcg(&a.gen.cnt->iteration);
+            const int per = (zcount + n_sweep - 1) / n_sweep;
+            for (int k = PERSIST_THREADS - 1 - tid; k < per; k += PERSIST_THREADS) {
+                const int e = blockIdx.x * per + k;
+                if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_normal(a.gen.seed, iter + 1, STREAM_PROPOSAL, (unsigned long long)e);
+            }
+        }
+        for (int s = 0; s < nseg; ++s) {
+            const int node_base = seg_tile[s] * PT;
+            for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {
+                int node = node_base + i / 3, j = i - (i / 3) * 3;
+                float v = (node < a.P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
+                sprops[i] = v;
+                if (j == 2) sscl[i / 3] = (node < a.P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+            }
+            __syncthreads();
+            if (s == 0) PMP_STAMP(dbg, 2);
+            float b0[R], b1[R]; double scl[R]; unsigned long long accq[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { int i = tp * R + r; b0[r] = sprops[3 * i]; b1[r] = sprops[3 * i + 1]; scl[r] = sscl[i]; accq[r] = 0ull; }
+            const int nct = (int)(seg_c1[s] - seg_c0[s]);
+            for (int c = td; c < nct; c += TD) {
+                int cnt = (int)min((long long)CHUNK, a.n_local - (seg_c0[s] + c) * CHUNK);
+                float part[R];
+                const float* sx = tile + (size_t)(seg_slot[s] + c) * CHUNK_STRIDE;
+                chunk_sumsq<R, true>(sx, sx + CHUNK, cnt, b0, b1, part);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double dq = (double)part[r] * scl[r];
+                    if (!(dq < a.sat_limit)) { dq = a.sat_limit; saturated = true; }
+                    accq[r] += (unsigned long long)__double2ll_rn(dq);
+                }
+            }
+            if (s == 0) PMP_STAMP(dbg, 3);
+#pragma unroll
+            for (int r = 0; r < R; ++r) sred[td * PT + tp * R + r] = accq[r];
+            __syncthreads();
+            for (int i = tid; i < PT; i += PERSIST_THREADS) {
+                unsigned long long sum = 0ull;
+                for (int k = 0; k < TD; ++k) sum += sred[k * PT + i];
+                if (node_base + i < a.P && sum) atomicAdd(a.acc + node_base + i, sum);
+            }
+            __syncthreads();
+        }
+        PMP_STAMP(dbg, 4);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(&pa.sync->arrive, 1u);
+        PMP_STAMP(dbg, 5);
+    }
+    if (saturated) atomicOr(&a.cnt->flags, 1);
+}
+
+}  // namespace pmp

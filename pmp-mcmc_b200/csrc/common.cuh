@@ -84,6 +84,7 @@ struct pmp_ctx {
     pmp::DeviceCounters* d_cnt = nullptr;
     float* d_z = nullptr;              // [2, P*dim] prefetched standard normals (current / next iteration)
     unsigned long long* d_dbg = nullptr; // optional phase stamps
+    void* d_psync = nullptr;           // PersistSync of the cooperative chain kernel
     unsigned int* d_done = nullptr;    // CTA completion counter of the fused sweep+accept kernel
     unsigned long long host_iter = 0;  // host mirror of d_cnt->iteration
     long long z_valid_iter = -1;       // iteration whose normals are in d_z, -1: none

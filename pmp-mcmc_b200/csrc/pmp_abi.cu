@@ -8,6 +8,7 @@
 
 #include "accept.cuh"
 #include "accept_fast.cuh"
+#include "chain_persistent.cuh"
 #include "common.cuh"
 #include "sweep_linear.cuh"
 
@@ -279,7 +280,7 @@ int pmp_destroy(pmp_ctx* c) {
     pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
-                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg};
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -565,6 +566,54 @@ int pmp_read_trace(pmp_ctx* c, int64_t max_iters, float* state, int32_t* next, i
     return PMP_OK;
 }
 
+// Persistent cooperative chain loop (chain_persistent.cuh): single GPU, linear-Gaussian target, fast-acceptance rules, and a
+// data slice per CTA that fits shared memory.  Returns 1 when it ran, 0 when the stepwise path must be used, < 0 on error.
+static int try_run_persistent(pmp_ctx* c, int64_t iters) {
+    if (!env_int("PMP_PERSISTENT", 1) || c->world != 1 || !fast_accept_ok(c) || iters < 2 || iters > 2000000000ll) return 0;
+    if (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) return 0;
+    const int G = c->sm_count;                                     // one CTA per SM; the last one is the acceptance CTA
+    const int n_sweep = G - 1;
+    const long long nchunks = (c->n_local + CHUNK - 1) / CHUNK;
+    if (nchunks == 0 || n_sweep < 1) return 0;
+    const int ntiles = (c->P + PERSIST_PT - 1) / PERSIST_PT;
+    const long long units = (long long)ntiles * nchunks;
+    const long long max_chunks = (units + n_sweep - 1) / n_sweep + 1;
+    const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
+    const size_t accept_smem = (size_t)c->P * (c->cfg.algo == PMP_ALGO_PSP ? 4 : 2) * sizeof(double);
+    const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
+    if (smem > 200 * 1024) return 0;
+    if (!c->d_psync) { PMP_CUDA(cudaMalloc((void**)&c->d_psync, sizeof(PersistSync))); }
+    PMP_CUDA(cudaMemsetAsync(c->d_psync, 0, sizeof(PersistSync), c->stream));
+    int rc;
+    if ((rc = launch_propose(c))) return rc;                       // nodes of the first iteration; later ones come from the acceptance CTA
+    PersistArgs pa{};
+    pa.sw = SweepArgs{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, PERSIST_TP, PERSIST_TD, sat_limit(c), 1, c->d_z,
+                      ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, 0},
+                      c->d_dbg};
+    pa.fa = AcceptFastArgs{make_accept_args(c, 1, 0, 1, nullptr), c->d_z, 1,
+                           ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, 0}};
+    pa.sync = reinterpret_cast<PersistSync*>(c->d_psync);
+    pa.iters = (int)iters;
+    pa.max_chunks = (int)max_chunks;
+    void* kargs[] = {&pa};
+    const void* fn;
+    switch (c->cfg.algo) {
+        case PMP_ALGO_MP: fn = (const void*)chain_persistent_kernel<PMP_ALGO_MP>; break;
+        case PMP_ALGO_PSP: fn = (const void*)chain_persistent_kernel<PMP_ALGO_PSP>; break;
+        default: fn = (const void*)chain_persistent_kernel<PMP_ALGO_TABLE>; break;
+    }
+    PMP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, smem));
+    if (per_sm < 1) return 0;
+    PMP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PERSIST_THREADS), kargs, smem, c->stream));
+    c->launches++;
+    c->host_iter += (unsigned long long)iters;
+    c->z_valid_iter = -1;
+    c->lt_valid = false;
+    return 1;
+}
+
 // The chain loop.  A CUDA graph of GRAPH_ITERS iterations is captured once per configuration and replayed, so the
 // host issues one launch per GRAPH_ITERS iterations; the iteration counter, the state and the trace cursor live on the
 // device, so replay needs no parameter update.
@@ -574,6 +623,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
     PMP_CUDA(cudaSetDevice(c->device));
     const int GI = env_int("PMP_GRAPH_ITERS", 32);
     int rc;
+    if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS) { rc = try_run_persistent(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK; }
     int64_t done = 0;
     if (GI > 1 && iters >= GI) {
         if (!c->graph_exec || c->graph_iters != GI) {

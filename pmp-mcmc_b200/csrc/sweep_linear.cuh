@@ -37,6 +37,9 @@ struct SweepArgs {
 };
 
 constexpr int SWEEP_THREADS = 256;
+#ifndef SWEEP_MIN_CTAS
+#define SWEEP_MIN_CTAS 4
+#endif
 constexpr int TILE_CHUNKS = 32;                    // chunks staged per shared-memory buffer (3072 points, 24.75 KB)
 constexpr int MAX_TP = 64;                         // node tile <= 256 nodes
 constexpr int CHUNK_STRIDE = 2 * CHUNK + 4;        // floats per staged chunk: x[CHUNK], y[CHUNK], 16 B pad (bank skew)
@@ -152,7 +155,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // the first stage is issued before anything that depends on the chain state, so its latency hides behind the
 // construction of the tile's nodes.
 template <int R, bool PACKED>
-__global__ void __launch_bounds__(SWEEP_THREADS, 3) sweep_linear_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_CTAS) sweep_linear_kernel(const __grid_constant__ SweepArgs a) {
     extern __shared__ __align__(16) float tile[];                 // 2 x TILE_CHUNKS x CHUNK_STRIDE floats
     __shared__ float sprops[MAX_TP * R * 3];                      // the tile's nodes (b0, b1, sigma)
     __shared__ double sscl[MAX_TP * R];                           // 2^FX_SHIFT / sigma^2 per node
@@ -251,9 +254,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 3) sweep_linear_kernel(const __
             // ever waits for a binary64 quantile evaluation
             const unsigned long long iter = a.gen.cnt->iteration;
             const int per = (zcount + gridDim.x - 1) / gridDim.x;
-            const int k = SWEEP_THREADS - 1 - tid, e = blockIdx.x * per + k;
-            if (k < per && e < zcount)
-                a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+            for (int k = SWEEP_THREADS - 1 - tid; k < per; k += SWEEP_THREADS) {      // per > SWEEP_THREADS when the grid is small (few units)
+                const int e = blockIdx.x * per + k;
+                if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+            }
         }
         first_segment = false;
         // ---- segment flush, integer adds only: lanes that share a node (warp shuffles) → one row per warp in shared

@@ -37,18 +37,12 @@ def bench(label, iters=2000):
     print("%-40s %8.2f us/iter (graph)  | plain launches %8.2f us/iter, sweep kernel %7.2f us" % (label, ms / iters * 1e3, ms2 / min(iters, 1000) * 1e3, sw / min(iters, 1000) * 1e3), flush=True)
 
 for tp in (16, 32, 64):
-    for per_sm in (2, 3):
+    for per_sm in (2, 3, 4):
         os.environ["PMP_SWEEP_TP"] = str(tp); os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = str(per_sm)
         c.trace_config(0, 0)  # drops the cached graph
-        bench("P=1024 n=100k TP=%d per_sm=%d" % (tp, per_sm))
-os.environ["PMP_SWEEP_TP"] = "16"; os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = "3"
-os.environ["PMP_ACCEPT_GENERIC"] = "1"; c.trace_config(0, 0); bench("TP=16 per_sm=3 generic accept + propose kernels")
-os.environ["PMP_ACCEPT_GENERIC"] = "0"
-os.environ["PMP_SWEEP_SCALAR"] = "1"; c.trace_config(0, 0); bench("TP=16 per_sm=3 scalar FFMA")
-os.environ["PMP_SWEEP_SCALAR"] = "0"
-for gi in (1, 32):
-    os.environ["PMP_GRAPH_ITERS"] = str(gi); c.trace_config(0, 0)
-    bench("graph_iters=%d" % gi)
+        c.propose(); sw = c.time_sweep(200) / 200 * 1e3
+        bench("P=1024 n=100k TP=%d per_sm=%d [sweep b2b %.2f us]" % (tp, per_sm, sw))
+os.environ["PMP_SWEEP_TP"] = "32"; os.environ["PMP_SWEEP_BLOCKS_PER_SM"] = "2"
 os.environ["PMP_GRAPH_ITERS"] = "32"
 # binary tree D=10 PSP python draw
 c.configure(L.TREE_BINARY, depth=10, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_PSP, draw=L.DRAW_PYTHON, alpha=0.01, scale=2000.0)

@@ -105,19 +105,21 @@ def test_single_proposal_rules(ctx, algo, u, lt, expect):
     assert np.array_equal(ctx.get_state(), props[expect])
 
 
-@pytest.mark.parametrize("tree,b,depth,algo,draw,flags,scale", [(0, 1024, 1, "MP", "CUDA", 0, 1000.0), (0, 4, 1, "MP", "PYTHON", 0, 10.0), (1, 2, 10, "PSP", "PYTHON", 0, 2000.0),
-                                                                (1, 2, 3, "PSP", "PYTHON", 0, 2000.0), (1, 2, 10, "TABLE", "CUDA", "CONST", 1000.0), (2, 8, 2, "PMP", "PYTHON", 0, 2000.0),
-                                                                (0, 2000, 1, "MP", "CUDA", 0, 2000.0)])
-@pytest.mark.parametrize("generic", [0, 1])
-def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, flags, scale, generic, monkeypatch):
+@pytest.mark.parametrize("tree,b,depth,algo,draw,flags,scale,n", [(0, 1024, 1, "MP", "CUDA", 0, 1000.0, 20000), (0, 4, 1, "MP", "PYTHON", 0, 10.0, 20000), (1, 2, 10, "PSP", "PYTHON", 0, 2000.0, 20000),
+                                                                  (1, 2, 3, "PSP", "PYTHON", 0, 2000.0, 20000), (1, 2, 10, "TABLE", "CUDA", "CONST", 1000.0, 20000), (2, 8, 2, "PMP", "PYTHON", 0, 2000.0, 20000),
+                                                                  (0, 2000, 1, "MP", "CUDA", 0, 2000.0, 20000), (0, 1024, 1, "MP", "CUDA", 0, 10.0, 500), (0, 4, 1, "MP", "CUDA", 0, 10.0, 500),
+                                                                  (1, 2, 10, "PSP", "PYTHON", 0, 10.0, 500)])
+@pytest.mark.parametrize("generic,persistent", [(0, 1), (0, 0), (1, 0)])
+def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, flags, scale, n, generic, persistent, monkeypatch):
     """pmp_run (device-resident loop: fused sweep, acceptance kernel that also publishes the next nodes, CUDA graph) against a
     step-by-step oracle replay: same proposals (bit-exact), log-weights within 1e-6 relative, identical draw and accepted
-    index sequences, identical states.  `generic` switches the acceptance to the general kernel."""
+    index sequences, identical states.  `generic` switches the acceptance to the general kernel, `persistent` the loop structure."""
     import pmp_mcmc_b200 as pm
     L, o = _L(), _o()
     monkeypatch.setenv("PMP_ACCEPT_GENERIC", str(generic))
+    monkeypatch.setenv("PMP_PERSISTENT", str(persistent))     # 1: one cooperative kernel for the whole chain; 0: CUDA-graph replay of sweep + acceptance
     monkeypatch.setenv("PMP_GRAPH_ITERS", "8")
-    n, iters, seed = 20000, 13, 77
+    iters, seed = 13, 77
     x, y = synthetic_linear(n, seed=5)
     fl = L.FLAG_QUIRK_TABLE_CONST if flags == "CONST" else 0
     c = pm.Context(0)
@@ -152,3 +154,30 @@ def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, fla
         assert np.array_equal(c.get_state(), state)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("n,P", [(500, 4), (500, 1024), (64, 16), (100000, 4), (5000, 3000)])
+def test_loop_structures_agree(n, P, monkeypatch):
+    """The persistent cooperative kernel and the CUDA-graph replay of sweep + acceptance are two schedules of the same
+    arithmetic: identical states, accepted indices and log-weight bits after the same number of iterations — also when
+    there are fewer (tile, chunk) units than sweep CTAs (n = 500: 8 chunks) or more nodes than one CTA's tile."""
+    import pmp_mcmc_b200 as pm
+    L = _L()
+    x, y = synthetic_linear(n, seed=9)
+    out = []
+    for persistent in (1, 0):
+        monkeypatch.setenv("PMP_PERSISTENT", str(persistent))
+        c = pm.Context(0)
+        try:
+            c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.01, scale=max(n / 50.0, 1.0))
+            c.set_data_linear(x, y); c.set_state([1, 1, 1]); c.seed(21, 0)
+            c.trace_config(70, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_LOGW)
+            c.run(70)
+            tr = c.read_trace()
+            out.append((c.get_state().copy(), tr["next"].copy(), tr["logw"].copy(), tr["state"].copy()))
+        finally:
+            c.close()
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2].view(np.uint64), out[1][2].view(np.uint64))
+    assert np.array_equal(out[0][3].view(np.uint32), out[1][3].view(np.uint32))
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
