@@ -70,6 +70,7 @@ struct pmp_ctx {
 
     // linear-Gaussian data shard
     float* d_x = nullptr; float* d_y = nullptr;
+    uint8_t* d_bimg = nullptr;         // [nchunks][2048] bf16 data operand image of the tensor-core sweep (sweep_linear_tc.cuh)
     long long n_local = 0, n_offset = 0, n_global = 0;
 
     // chain

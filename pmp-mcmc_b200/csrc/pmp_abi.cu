@@ -11,6 +11,7 @@
 #include "chain_persistent.cuh"
 #include "common.cuh"
 #include "sweep_linear.cuh"
+#include "sweep_linear_tc.cuh"
 
 namespace pmp {
 
@@ -96,9 +97,40 @@ static AcceptArgs make_accept_args(pmp_ctx* c, int from_acc, int only_finalize, 
     return a;
 }
 
+// Tensor-core sweep (sweep_linear_tc.cuh) when its shared-memory plan fits: node operand + integer scratch for all of
+// P, and this CTA's chunks resident.  Returns the grid size, 0 when the FMA sweep must be used.
+static int tc_sweep_plan(const pmp_ctx* c, int ctas, int* max_chunks, int* max_units, size_t* smem) {
+    if (env_int("PMP_SWEEP_FMA", 0) || !c->d_bimg) return 0;
+    const int ntiles = (c->P + tc::TILE_NODES - 1) / tc::TILE_NODES;
+    const long long nchunks = (c->n_local + CHUNK - 1) / CHUNK;
+    if (ntiles > tc::MAX_TILES || nchunks == 0) return 0;
+    const long long units = nchunks * ntiles;
+    long long g = ctas < units ? ctas : units;
+    const long long per = (units + g - 1) / g;
+    const long long mc = (per + ntiles - 1) / ntiles + 1;
+    if (per > tc::MAX_UNITS) return 0;
+    const size_t bytes = tc::smem_bytes(ntiles, (int)mc, (int)per);
+    if (bytes > 200 * 1024) return 0;
+    *max_chunks = (int)mc; *max_units = (int)per; *smem = bytes;
+    return (int)g;
+}
+
 // generate: also fill the next iteration's half of the normals table as a side job.
 static int launch_sweep_linear(pmp_ctx* c, int generate) {
     PMP_REQUIRE(c->d_x && c->n_local >= 0, "linear-Gaussian data not set (pmp_set_data_linear)");
+    {
+        int mc = 0, mu = 0; size_t smem = 0;
+        const int g = tc_sweep_plan(c, c->sm_count, &mc, &mu, &smem);
+        if (g > 0) {
+            tc::Args ta{c->d_bimg, c->d_props, c->d_acc, c->d_cnt, (c->n_local + CHUNK - 1) / CHUNK, c->P, mc, mu, sat_limit(c), generate, c->d_z,
+                        ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0},
+                        c->d_dbg};
+            tc::sweep_linear_tc_kernel<<<(unsigned)g, tc::STANDALONE_THREADS, smem, c->stream>>>(ta);
+            c->launches++;
+            PMP_CUDA(cudaGetLastError());
+            return PMP_OK;
+        }
+    }
     constexpr int R = 4;
     int need = (c->P + R - 1) / R;
     int tp_cap = env_int("PMP_SWEEP_TP", 32);
@@ -248,6 +280,7 @@ int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* 
     PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_PSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
     PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_PMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
     PMP_CUDA(cudaFuncSetAttribute(accept_kernel<PMP_ALGO_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(tc::sweep_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PMP_CUDA(cudaFuncSetAttribute(sweep_linear_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes()));
     PMP_CUDA(cudaFuncSetAttribute(sweep_linear_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes()));
     // without this the driver may pick a carveout that fits a single CTA per SM
@@ -280,7 +313,7 @@ int pmp_destroy(pmp_ctx* c) {
     pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
-                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync};
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_bimg};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -376,6 +409,14 @@ int pmp_set_data_linear(pmp_ctx* c, const float* x, const float* y, int64_t n_lo
     if (n_local) {
         PMP_CUDA(cudaMemcpyAsync(c->d_x, x, n_local * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         PMP_CUDA(cudaMemcpyAsync(c->d_y, y, n_local * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    // data operand of the tensor-core sweep: the shared-memory image of every 64-point chunk, written once
+    const long long nchunks = ((long long)n_local + CHUNK - 1) / CHUNK;
+    if ((rc = dev_alloc(&c->d_bimg, (size_t)nchunks * tc::CHUNK_BYTES))) return rc;
+    if (nchunks) {
+        tc::build_data_image_kernel<<<(unsigned)((nchunks * CHUNK + 255) / 256), 256, 0, c->stream>>>(c->d_x, c->d_y, n_local, nchunks, c->d_bimg);
+        c->launches++;
+        PMP_CUDA(cudaGetLastError());
     }
     PMP_CUDA(cudaStreamSynchronize(c->stream));
     c->n_local = n_local; c->n_offset = n_offset; c->n_global = n_global;
