@@ -13,7 +13,7 @@
 //   * the two hand-offs per iteration are release/acquire counters in global memory (bounded spins: a protocol bug
 //     traps instead of hanging the GPU).
 #pragma once
-#include "accept_fast.cuh"
+#include "accept_lean.cuh"
 #include "sweep_linear.cuh"
 
 namespace pmp {
@@ -48,16 +48,24 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     const int n_sweep = gridDim.x - 1;
 
     if ((int)blockIdx.x == n_sweep) {
-        // ================= acceptance CTA =================
+        // ================= acceptance CTA: pre (during the sweep) → wait → crit → release → post (during the next sweep) =====
+        __shared__ double red[4][32];
+        __shared__ int s_pick;
+        const LeanSmem ls = lean_carve(dsm, pa.fa.base.P, ALGO);
+        LeanRegs lr;
         for (int it = 0; it < pa.iters; ++it) {
+            lean_pre<ALGO>(pa.fa, ls, lr, red, &s_pick, 1);
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 8] = clock64(); pa.fa.base.dbg[32 + 24] = globaltimer_ns(); }
             if (tid == 0) spin_until_ge(&pa.sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
             __syncthreads();
-            accept_fast_body<ALGO>(pa.fa, reinterpret_cast<double*>(dsm));
+            lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick);
             __threadfence();
             __syncthreads();
             if (tid == 0) st_release(&pa.sync->version, (unsigned)(it + 1));
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 9] = clock64(); pa.fa.base.dbg[32 + 25] = globaltimer_ns(); }
+            lean_post<ALGO>(pa.fa, ls, lr);
+            __threadfence();          // trace cursor and state are read back by the next pre / by the host
+            __syncthreads();
         }
         return;
     }
@@ -74,7 +82,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     const int ntiles = (a.P + PT - 1) / PT;
     const long long units = (long long)ntiles * a.nchunks;
     const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
-    const int zcount = a.P * 3;
 
     // ---- stage this CTA's data slice once: segment s covers chunks [c_begin, c_end) of node tile ptile -----------------
     int nseg = 0; int seg_tile[3]; long long seg_c0[3], seg_c1[3]; int seg_slot[3];
@@ -105,14 +112,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
         if (tid == 0 && it > 0) spin_until_ge(&pa.sync->version, (unsigned)it);
         __syncthreads();
         PMP_STAMP(dbg, 1);
-        if (a.generate) {   // side job of the last warps: this CTA's slice of the NEXT iteration's normals (every CTA, also one without units)
-            const unsigned long long iter = __ldcg(&a.gen.cnt->iteration);
-            const int per = (zcount + n_sweep - 1) / n_sweep;
-            for (int k = PERSIST_THREADS - 1 - tid; k < per; k += PERSIST_THREADS) {
-                const int e = blockIdx.x * per + k;
-                if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_normal(a.gen.seed, iter + 1, STREAM_PROPOSAL, (unsigned long long)e);
-            }
-        }
         for (int s = 0; s < nseg; ++s) {
             const int node_base = seg_tile[s] * PT;
             for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {

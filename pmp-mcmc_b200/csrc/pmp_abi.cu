@@ -8,6 +8,7 @@
 
 #include "accept.cuh"
 #include "accept_fast.cuh"
+#include "accept_lean.cuh"
 #include "chain_persistent.cuh"
 #include "common.cuh"
 #include "sweep_linear.cuh"
@@ -100,7 +101,7 @@ static AcceptArgs make_accept_args(pmp_ctx* c, int from_acc, int only_finalize, 
 // Tensor-core sweep (sweep_linear_tc.cuh) when its shared-memory plan fits: node operand + integer scratch for all of
 // P, and this CTA's chunks resident.  Returns the grid size, 0 when the FMA sweep must be used.
 static int tc_sweep_plan(const pmp_ctx* c, int ctas, int* max_chunks, int* max_units, size_t* smem) {
-    if (env_int("PMP_SWEEP_FMA", 0) || !c->d_bimg) return 0;
+    if (!env_int("PMP_SWEEP_TC", 0) || !c->d_bimg) return 0;     // opt-in until it beats the FMA sweep
     const int ntiles = (c->P + tc::TILE_NODES - 1) / tc::TILE_NODES;
     const long long nchunks = (c->n_local + CHUNK - 1) / CHUNK;
     if (ntiles > tc::MAX_TILES || nchunks == 0) return 0;
@@ -186,9 +187,22 @@ static bool fast_accept_ok(const pmp_ctx* c) {
     return c->cfg.algo == PMP_ALGO_TABLE && ((c->cfg.flags & (PMP_FLAG_QUIRK_TABLE_CONST | PMP_FLAG_NO_KERNEL_TERM)) != 0) && !(c->cfg.flags & PMP_FLAG_STANDARDIZE);
 }
 
+static bool lean_accept_ok(const pmp_ctx* c) { return fast_accept_ok(c) && c->P <= LEAN_MAX_P && env_int("PMP_ACCEPT_LEAN", 1); }
+
 static int launch_accept_fast(pmp_ctx* c, int make_next) {
     AcceptFastArgs fa{make_accept_args(c, 1, 0, 1, nullptr), c->d_z, make_next,
                       ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0}};
+    if (lean_accept_ok(c)) {     // three-phase acceptance (accept_lean.cuh); same rules, shorter critical path
+        const size_t lsm = lean_smem_bytes(c->P, c->cfg.algo);
+        switch (c->cfg.algo) {
+            case PMP_ALGO_MP: accept_lean_kernel<PMP_ALGO_MP><<<1, ACCEPT_THREADS, lsm, c->stream>>>(fa); break;
+            case PMP_ALGO_PSP: accept_lean_kernel<PMP_ALGO_PSP><<<1, ACCEPT_THREADS, lsm, c->stream>>>(fa); break;
+            default: accept_lean_kernel<PMP_ALGO_TABLE><<<1, ACCEPT_THREADS, lsm, c->stream>>>(fa); break;
+        }
+        c->launches++;
+        PMP_CUDA(cudaGetLastError());
+        return PMP_OK;
+    }
     size_t smem = (size_t)c->P * (c->cfg.algo == PMP_ALGO_PSP ? 4 : 2) * sizeof(double);
     switch (c->cfg.algo) {
         case PMP_ALGO_MP: accept_fast_kernel<PMP_ALGO_MP><<<1, ACCEPT_THREADS, smem, c->stream>>>(fa); break;
@@ -289,6 +303,9 @@ int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* 
     PMP_CUDA(cudaFuncSetAttribute(accept_fast_kernel<PMP_ALGO_MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
     PMP_CUDA(cudaFuncSetAttribute(accept_fast_kernel<PMP_ALGO_PSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * accept_smem > 220 * 1024 ? 220 * 1024 : 2 * accept_smem));
     PMP_CUDA(cudaFuncSetAttribute(accept_fast_kernel<PMP_ALGO_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, accept_smem));
+    PMP_CUDA(cudaFuncSetAttribute(accept_lean_kernel<PMP_ALGO_MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(LEAN_MAX_P, PMP_ALGO_MP)));
+    PMP_CUDA(cudaFuncSetAttribute(accept_lean_kernel<PMP_ALGO_PSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(LEAN_MAX_P, PMP_ALGO_PSP)));
+    PMP_CUDA(cudaFuncSetAttribute(accept_lean_kernel<PMP_ALGO_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(LEAN_MAX_P, PMP_ALGO_TABLE)));
     if (world_size > 1) {
         PMP_REQUIRE(nccl_unique_id, "world_size > 1 needs an NCCL unique id");
         int rc = load_nccl(); if (rc) { delete c; return rc; }
@@ -620,7 +637,8 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     const long long units = (long long)ntiles * nchunks;
     const long long max_chunks = (units + n_sweep - 1) / n_sweep + 1;
     const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
-    const size_t accept_smem = (size_t)c->P * (c->cfg.algo == PMP_ALGO_PSP ? 4 : 2) * sizeof(double);
+    if (!lean_accept_ok(c)) return 0;
+    const size_t accept_smem = lean_smem_bytes(c->P, c->cfg.algo);
     const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
     if (smem > 200 * 1024) return 0;
     if (!c->d_psync) { PMP_CUDA(cudaMalloc((void**)&c->d_psync, sizeof(PersistSync))); }
@@ -628,7 +646,7 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     int rc;
     if ((rc = launch_propose(c))) return rc;                       // nodes of the first iteration; later ones come from the acceptance CTA
     PersistArgs pa{};
-    pa.sw = SweepArgs{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, PERSIST_TP, PERSIST_TD, sat_limit(c), 1, c->d_z,
+    pa.sw = SweepArgs{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, PERSIST_TP, PERSIST_TD, sat_limit(c), 0, c->d_z,
                       ProposeArgs{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, 0},
                       c->d_dbg};
     pa.fa = AcceptFastArgs{make_accept_args(c, 1, 0, 1, nullptr), c->d_z, 1,

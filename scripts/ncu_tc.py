@@ -1,5 +1,6 @@
 """A few launches of the tensor-core sweep at the C3 shape (P=1024, n=100k) for ncu."""
 import os, sys
+os.environ.setdefault("PMP_SWEEP_TC", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np

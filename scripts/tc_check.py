@@ -18,11 +18,11 @@ for n, P, scale in ((100000, 1024, 1000.0), (500, 1024, 10.0), (500, 4, 10.0), (
         lt64 = o.loglik_linear_f64(x, y, props, scale)
         res = {}
         for fma in (0, 1):
-            os.environ["PMP_SWEEP_FMA"] = str(fma)
+            os.environ["PMP_SWEEP_TC"] = str(1 - fma)
             lt = c.loglik()
             lt2 = c.loglik()
             us = c.time_sweep(200) / 200 * 1e3
             res[fma] = (lt, us)
             print("n=%d P=%d state=%s %s: rel err vs f64 max %.2e  deterministic %s  sweep b2b %.2f us" % (n, P, state, "fma" if fma else "tc ", np.max(np.abs(lt - lt64) / np.abs(lt64)), np.array_equal(lt, lt2), us), flush=True)
         print("    tc vs fma max rel %.2e" % np.max(np.abs(res[0][0] - res[1][0]) / np.abs(res[1][0])))
-os.environ["PMP_SWEEP_FMA"] = "0"
+os.environ["PMP_SWEEP_TC"] = "0"

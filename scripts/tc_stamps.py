@@ -1,5 +1,6 @@
 """Phase stamps of the tensor-core sweep kernel (CTA 0) and the per-CTA start/end spread."""
-import os, sys, ctypes
+import os, sys
+os.environ.setdefault("PMP_SWEEP_TC", "1"), ctypes
 os.environ["PMP_DEBUG_STAMPS"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

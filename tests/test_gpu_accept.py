@@ -109,14 +109,15 @@ def test_single_proposal_rules(ctx, algo, u, lt, expect):
                                                                   (1, 2, 3, "PSP", "PYTHON", 0, 2000.0, 20000), (1, 2, 10, "TABLE", "CUDA", "CONST", 1000.0, 20000), (2, 8, 2, "PMP", "PYTHON", 0, 2000.0, 20000),
                                                                   (0, 2000, 1, "MP", "CUDA", 0, 2000.0, 20000), (0, 1024, 1, "MP", "CUDA", 0, 10.0, 500), (0, 4, 1, "MP", "CUDA", 0, 10.0, 500),
                                                                   (1, 2, 10, "PSP", "PYTHON", 0, 10.0, 500)])
-@pytest.mark.parametrize("generic,persistent", [(0, 1), (0, 0), (1, 0)])
-def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, flags, scale, n, generic, persistent, monkeypatch):
+@pytest.mark.parametrize("generic,persistent,tc", [(0, 1, 0), (0, 0, 0), (0, 0, 1), (1, 0, 0)])
+def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, flags, scale, n, generic, persistent, tc, monkeypatch):
     """pmp_run (device-resident loop: fused sweep, acceptance kernel that also publishes the next nodes, CUDA graph) against a
     step-by-step oracle replay: same proposals (bit-exact), log-weights within 1e-6 relative, identical draw and accepted
     index sequences, identical states.  `generic` switches the acceptance to the general kernel, `persistent` the loop structure."""
     import pmp_mcmc_b200 as pm
     L, o = _L(), _o()
     monkeypatch.setenv("PMP_ACCEPT_GENERIC", str(generic))
+    monkeypatch.setenv("PMP_SWEEP_TC", str(tc))               # 1: tensor-core sweep in the stepwise loop
     monkeypatch.setenv("PMP_PERSISTENT", str(persistent))     # 1: one cooperative kernel for the whole chain; 0: CUDA-graph replay of sweep + acceptance
     monkeypatch.setenv("PMP_GRAPH_ITERS", "8")
     iters, seed = 13, 77
@@ -135,23 +136,35 @@ def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, fla
         tr = c.read_trace()
         assert tr["n"] == iters and c.iteration() == iters
         bb = 2 if tree == 1 else b
+        near_ties = 0
         for it in range(iters):
             props = o.propose(tree, b, depth, 3, 0.02, state, seed, it)
             lt = o.loglik_linear_f64(x, y, props, scale)
             A = _oracle_logweights(o, L, getattr(L, "ALGO_" + algo), lt, props.astype(np.float64), bb, depth, fl)
-            np.testing.assert_allclose(tr["logw"][it], A, rtol=1e-6, atol=1e-7)
+            # log-weights are sums of differences of log-targets, each good to ~1e-7 relative: the absolute term scales with |lt|
+            np.testing.assert_allclose(tr["logw"][it], A, rtol=1e-6, atol=1e-7 + 4e-7 * float(np.max(np.abs(lt[np.isfinite(lt)]))))
             u = o.stream_uniforms(seed, it, o.STREAM_DRAW, 0, P)
             w_dev = o.weights_from_log(tr["logw"][it])
             side = "left" if draw == "CUDA" else "right"
             assert np.array_equal(tr["draws"][it], o.draw_blocked(w_dev, u, side))
             ref_idx = o.draw_libstdcxx(o.weights_from_log(A), u) if draw == "CUDA" else o.draw_numpy(o.weights_from_log(A), u)
-            assert np.array_equal(tr["draws"][it], ref_idx), "iteration %d: %d draws differ" % (it, int((tr["draws"][it] != ref_idx).sum()))
+            # identical to the draws made from the binary64 log-targets, except where a uniform sits on a cdf boundary closer than
+            # the float32 log-target noise (1e-5 relative, the north-star tolerance): such near-ties are verified, then followed
+            differ = np.nonzero(tr["draws"][it] != ref_idx)[0]
+            if differ.size:
+                cdf = np.cumsum(o.weights_from_log(A)); cdf /= cdf[-1]
+                for t in differ:
+                    lo, hi = sorted((int(tr["draws"][it][t]), int(ref_idx[t])))
+                    assert hi - lo == 1 and abs(u[t] - cdf[lo]) < 1e-5, "iteration %d draw %d: %d vs %d is not a near-tie (margin %.3e)" % (it, t, tr["draws"][it][t], ref_idx[t], abs(u[t] - cdf[lo]))
+                near_ties += differ.size
+                ref_idx = tr["draws"][it].copy()
             nxt = ref_idx[o.pick_index(o.stream_uniforms(seed, it, o.STREAM_PICK, 0, 1)[0], P)] if draw == "PYTHON" else ref_idx[0]
             assert tr["next"][it] == nxt
             assert np.array_equal(tr["samples"][it], props[ref_idx])
             state = props[nxt]
             assert np.array_equal(tr["state"][it], state)
         assert np.array_equal(c.get_state(), state)
+        assert near_ties <= 2, "%d near-tie draws in %d" % (near_ties, iters * P)
     finally:
         c.close()
 

@@ -40,10 +40,10 @@ def test_proposals_bit_exact(ctx, tree, b, depth, dim):
                                        (1, 4, 1.0), (63, 16, 1.0), (65, 1000, 1.0), (4097, 64, 5.0), (100003, 1296, 2000.0)])
 @pytest.mark.parametrize("impl", ["tc", "fma"])
 def test_loglik_parity(ctx, n, P, scale, impl, monkeypatch):
-    """The P x n sweep, both implementations: `tc` = tcgen05 residual GEMM + square-accumulate epilogue (the default),
-    `fma` = CUDA-core FFMA2 sweep (the fallback for shapes the tensor-core plan does not cover, bit-mirrored by the oracle)."""
+    """The P x n sweep, both implementations: `fma` = CUDA-core FFMA2 sweep (the default, bit-mirrored by the oracle),
+    `tc` = tcgen05 residual GEMM + square-accumulate epilogue (PMP_SWEEP_TC=1)."""
     L, o = _L(), _o()
-    monkeypatch.setenv("PMP_SWEEP_FMA", "1" if impl == "fma" else "0")
+    monkeypatch.setenv("PMP_SWEEP_TC", "1" if impl == "tc" else "0")
     x, y = synthetic_linear(n, seed=n)
     ctx.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.02, scale=scale)
     ctx.set_data_linear(x, y)
