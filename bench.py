@@ -183,45 +183,58 @@ def main():
         t0 = time.perf_counter()
         pdist.set_data_linear_sharded(ctx, xp, yp)                 # H2D: this rank's shard of x and y
         ctx.set_state([1, 1, 1]); ctx.seed(7, 0)
-        ctx.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT)
+        ctx.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS)
         ctx.run(iters)
-        tr = ctx.read_trace()                                       # D2H: the chain ([iters,3] float32 + [iters] int32)
+        tr = ctx.read_trace()                                       # D2H: states [iters,3] f32, accepted index [iters] i32, the P resampled indices [iters,P] i32
         dt = max_over_ranks(time.perf_counter() - t0)
         assert tr["n"] == iters
         if s >= 2:
             e2e_s.append(dt)
     e2e_value = args.steps * iters * P_NODES / sum(e2e_s)
     h2d = int((hi - lo) * 8 + 12)
-    d2h = int(iters * 16)
+    d2h = int(iters * (16 + 4 * P_NODES))
     ctx.trace_config(0, 0)
 
-    # ---- roofline of the dominant kernel (the sweep): algorithmic flops / average launch duration ---------------------
+    # ---- roofline of the dominant kernel: algorithmic flops / average launch duration ----------------------------------
+    # Single GPU: the whole chain is ONE cooperative launch (chain_persistent_kernel: 147 sweep CTAs + 1 acceptance CTA), so
+    # "the kernel's launch duration" is the timed region itself and the fraction below charges the sweep's roofline with the
+    # acceptance and the two hand-offs per iteration as well.  Multi-GPU: the stepwise loop, dominant kernel = sweep_linear_kernel.
+    flops_per_iter = 6.0 * (hi - lo) * P_NODES                   # 3 FP32 lane-ops (sub, fma, fma) per (node, point), DESIGN.md §4
+    peak = max(ctx.fp32_peak(False), ctx.fp32_peak(True))         # measured FFMA/FFMA2 issue-rate microbenchmark (MEASURED_PEAKS.json has no FP32 figure)
     ctx.set_state([1, 1, 1]); ctx.seed(2024, 0); ctx.propose()
     reps = 200
     sweep_ms = ctx.time_sweep(reps) / reps
-    flops_per_launch = 6.0 * (hi - lo) * P_NODES                 # 3 FP32 lane-ops (sub, fma, fma) per (node, point), DESIGN.md §4
-    achieved = flops_per_launch / (sweep_ms * 1e-3) / 1e12
-    peak = max(ctx.fp32_peak(False), ctx.fp32_peak(True))         # measured FFMA/FFMA2 issue-rate microbenchmark (MEASURED_PEAKS.json has no FP32 figure)
-    bytes_per_launch = 8.0 * (hi - lo) + 12.0 * P_NODES + 8.0 * P_NODES
+    sweep_achieved = flops_per_iter / (sweep_ms * 1e-3) / 1e12
+    bytes_per_iter = 8.0 * (hi - lo) + 12.0 * P_NODES + 8.0 * P_NODES
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    persistent = world == 1 and os.environ.get("PMP_PERSISTENT", "1") != "0"
+    iter_s = total_s / (args.steps * iters)
+    if persistent:
+        kernel, kernel_us, launch_flops = "chain_persistent_kernel<MP> (one launch per step)", iter_s * 1e6 * iters, flops_per_iter * iters
+    else:
+        kernel, kernel_us, launch_flops = "sweep_linear_kernel<4,true>", sweep_ms * 1e3, flops_per_iter
+    achieved = launch_flops / (kernel_us * 1e-6) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "measured in this run by pmp_fp32_peak (FFMA/FFMA2 microbenchmark); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                "kernel": "sweep_linear_kernel<4,true>", "kernel_us": sweep_ms * 1e3, "flops_per_launch": flops_per_launch,
-                "hbm": {"achieved_gbs": bytes_per_launch / (sweep_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "note": "0.8 MB of data per launch: L2-resident, HBM is not the bound"}}
+                "note": "the sweep is bound by FP32 issue (3 lane-ops per node-point pair), not by HBM (0.8 MB, L2/shared-memory resident) nor by the tensor pipe; see DESIGN.md 4",
+                "kernel": kernel, "kernel_us": kernel_us, "flops_per_launch": launch_flops,
+                "sweep_kernel_alone": {"kernel": "sweep_linear_kernel<4,true>", "kernel_us": sweep_ms * 1e3, "achieved": sweep_achieved, "frac": sweep_achieved / peak,
+                                       "what": "the stepwise loop's sweep kernel launched back to back (CUDA events on the ctx stream)"},
+                "hbm": {"achieved_gbs": bytes_per_iter / iter_s / 1e9, "peak_gbs": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "note": "0.8 MB of data per iteration: L2-resident, HBM is not the bound"}}
 
     line = None
     if rank == 0:
         cpu = None
         if world == 1:
-            v, cores, dt = cpu_port_evals_per_s(x, y, 2048)
+            v, cores, dt = cpu_port_evals_per_s(x, y, 40960)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "2048 proposal-evaluations at n=100000 (2 sweeps of P=1024) with the lb.py per-proposal torch loop, %.1f s" % dt}
+                   "sample": "40960 proposal-evaluations at n=100000 (40 sweeps of P=1024) with the lb.py per-proposal torch loop, %.1f s" % dt}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32", "data": "synthetic",
@@ -232,7 +245,7 @@ def main():
                            "baseline": "reference README.md:44, V100: (33473.53 + 1099.258) us per iteration at P=1024, n=100000"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "what": "set_data (pinned host x,y) + set_state + %d iterations + read_trace per step, wall clock" % iters},
+                        "what": "set_data (pinned host x,y) + set_state + %d iterations + read_trace (states, accepted indices and all P resampled indices per iteration) per step, wall clock" % iters},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     ctx.close()
