@@ -65,9 +65,14 @@ __device__ __forceinline__ float proposal_value_zs(const ProposeArgs& a, const f
     return v;
 }
 
-// gen_z: 1 = compute the next iteration's normals here (persistent kernel), 0 = read them from the table the sweep filled
+// Where the normals of the next iteration's nodes come from.  TABLE_PRE: the table the previous sweep KERNEL filled (stepwise
+// loop: it is complete before this kernel starts).  TABLE_CRIT: the table the sweep CTAs of the same persistent kernel fill
+// during the sweep — complete only once they have all arrived, so it is read at the start of the critical phase, in the
+// same L2 round trip as the sums.  GENERATE: computed here (3P quantile evaluations in binary64 on one SM: slow).
+enum { LEAN_Z_TABLE_PRE = 0, LEAN_Z_GENERATE = 1, LEAN_Z_TABLE_CRIT = 2 };
+
 template <int ALGO>
-__device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], int* s_pick, int gen_z) {
+__device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], int* s_pick, int z_mode) {
     const AcceptArgs& a = fa.base;
     const pmp_config& cfg = a.cfg;
     const int P = a.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -83,8 +88,8 @@ __device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSme
     }
     for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.props[g] = __ldcg(a.props + g);
     if (fa.make_next) {
-        if (gen_z) for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = (float)stream_step(fa.gen.seed, r.iter + 1, (unsigned long long)g, fa.gen.uniform);
-        else { const float* zn = fa.z + ((r.iter + 1) & 1) * (long long)(P * 3); for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = __ldcg(zn + g); }
+        if (z_mode == LEAN_Z_GENERATE) for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = (float)stream_step(fa.gen.seed, r.iter + 1, (unsigned long long)g, fa.gen.uniform);
+        else if (z_mode == LEAN_Z_TABLE_PRE) { const float* zn = fa.z + ((r.iter + 1) & 1) * (long long)(P * 3); for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = __ldcg(zn + g); }
     }
 #pragma unroll
     for (int k = 0; k < LEAN_K; ++k) {
@@ -136,7 +141,7 @@ __device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSme
 }
 
 template <int ALGO>
-__device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], const int* s_pick) {
+__device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], const int* s_pick, int z_mode) {
     const AcceptArgs& a = fa.base;
     const pmp_config& cfg = a.cfg;
     const int P = a.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -150,6 +155,14 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
     unsigned long long q[LEAN_K];
 #pragma unroll
     for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? __ldcg(a.acc + p) : 0ull; }
+    if (z_mode == LEAN_Z_TABLE_CRIT && fa.make_next) {       // same L2 round trip as the sums; first read after the block barriers below
+        const float* zn = fa.z + ((r.iter + 1) & 1) * (long long)(P * 3);
+        float zr[3 * LEAN_K];
+#pragma unroll
+        for (int k = 0; k < 3 * LEAN_K; ++k) { const int g = tid + k * ACCEPT_THREADS; zr[k] = (g < 3 * P) ? __ldcg(zn + g) : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 3 * LEAN_K; ++k) { const int g = tid + k * ACCEPT_THREADS; if (g < 3 * P) s.z[g] = zr[k]; }
+    }
     double mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < LEAN_K; ++k) {
@@ -308,8 +321,8 @@ __global__ void __launch_bounds__(ACCEPT_THREADS, 1) accept_lean_kernel(const __
     __shared__ int s_pick;
     const LeanSmem s = lean_carve(accept_lean_sm, fa.base.P, ALGO);
     LeanRegs r;
-    lean_pre<ALGO>(fa, s, r, red, &s_pick, 0);
-    lean_crit<ALGO>(fa, s, r, red, &s_pick);
+    lean_pre<ALGO>(fa, s, r, red, &s_pick, LEAN_Z_TABLE_PRE);
+    lean_crit<ALGO>(fa, s, r, red, &s_pick, LEAN_Z_TABLE_PRE);
     __syncthreads();
     lean_post<ALGO>(fa, s, r);
 }

@@ -54,11 +54,11 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
         const LeanSmem ls = lean_carve(dsm, pa.fa.base.P, ALGO);
         LeanRegs lr;
         for (int it = 0; it < pa.iters; ++it) {
-            lean_pre<ALGO>(pa.fa, ls, lr, red, &s_pick, 1);
+            lean_pre<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 8] = clock64(); pa.fa.base.dbg[32 + 24] = globaltimer_ns(); }
             if (tid == 0) spin_until_ge(&pa.sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
             __syncthreads();
-            lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick);
+            lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
             __threadfence();
             __syncthreads();
             if (tid == 0) st_release(&pa.sync->version, (unsigned)(it + 1));
@@ -106,12 +106,21 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     }
 
     bool saturated = false;
+    const unsigned long long iter0 = __ldcg(&a.cnt->iteration);      // read before the acceptance CTA can have advanced it (it waits for every sweep CTA first)
     for (int it = 0; it < pa.iters; ++it) {
         unsigned long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
         PMP_STAMP(dbg, 0);
         if (tid == 0 && it > 0) spin_until_ge(&pa.sync->version, (unsigned)it);
         __syncthreads();
         PMP_STAMP(dbg, 1);
+        {   // side job: this CTA's slice of the NEXT iteration's normals (they depend on counters only); read by the acceptance CTA
+            const int zcount = a.P * 3, per = (zcount + n_sweep - 1) / n_sweep;
+            const unsigned long long iter = iter0 + (unsigned long long)it;
+            for (int k = PERSIST_THREADS - 1 - tid; k < per; k += PERSIST_THREADS) {
+                const int e = blockIdx.x * per + k;
+                if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+            }
+        }
         for (int s = 0; s < nseg; ++s) {
             const int node_base = seg_tile[s] * PT;
             for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {

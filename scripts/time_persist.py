@@ -11,8 +11,8 @@ for n, P, scale in ((100000, 1024, 1000.0), (500, 1024, 10.0), (500, 4, 10.0), (
     x, y = synthetic_linear(n)
     c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.01, scale=scale)
     c.set_data_linear(x, y)
-    for persistent in (1, 0):
-        os.environ["PMP_PERSISTENT"] = str(persistent)
+    for persistent, ptc in ((1, 1), (1, 0), (0, 0)):
+        os.environ["PMP_PERSISTENT"] = str(persistent); os.environ["PMP_PERSISTENT_TC"] = str(ptc)
         c.trace_config(0, 0)
         c.set_state([1, 1, 1]); c.seed(1, 0)
         c.run(200)
@@ -20,4 +20,4 @@ for n, P, scale in ((100000, 1024, 1000.0), (500, 1024, 10.0), (500, 4, 10.0), (
         for rep in range(3):
             ms, _ = c.run_timed(4000)
             best = min(best, ms / 4000 * 1e3)
-        print("n=%d P=%d persistent=%d: %.2f us/iter  state %s" % (n, P, persistent, best, c.get_state()), flush=True)
+        print("n=%d P=%d persistent=%d tc=%d: %.2f us/iter  state %s" % (n, P, persistent, ptc, best, c.get_state()), flush=True)

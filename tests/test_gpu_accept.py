@@ -109,7 +109,7 @@ def test_single_proposal_rules(ctx, algo, u, lt, expect):
                                                                   (1, 2, 3, "PSP", "PYTHON", 0, 2000.0, 20000), (1, 2, 10, "TABLE", "CUDA", "CONST", 1000.0, 20000), (2, 8, 2, "PMP", "PYTHON", 0, 2000.0, 20000),
                                                                   (0, 2000, 1, "MP", "CUDA", 0, 2000.0, 20000), (0, 1024, 1, "MP", "CUDA", 0, 10.0, 500), (0, 4, 1, "MP", "CUDA", 0, 10.0, 500),
                                                                   (1, 2, 10, "PSP", "PYTHON", 0, 10.0, 500)])
-@pytest.mark.parametrize("generic,persistent,tc", [(0, 1, 0), (0, 0, 0), (0, 0, 1), (1, 0, 0)])
+@pytest.mark.parametrize("generic,persistent,tc", [(0, 1, 1), (0, 1, 0), (0, 0, 0), (0, 0, 1), (1, 0, 0)])
 def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, flags, scale, n, generic, persistent, tc, monkeypatch):
     """pmp_run (device-resident loop: fused sweep, acceptance kernel that also publishes the next nodes, CUDA graph) against a
     step-by-step oracle replay: same proposals (bit-exact), log-weights within 1e-6 relative, identical draw and accepted
@@ -117,7 +117,8 @@ def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, fla
     import pmp_mcmc_b200 as pm
     L, o = _L(), _o()
     monkeypatch.setenv("PMP_ACCEPT_GENERIC", str(generic))
-    monkeypatch.setenv("PMP_SWEEP_TC", str(tc))               # 1: tensor-core sweep in the stepwise loop
+    monkeypatch.setenv("PMP_SWEEP_TC", str(tc))               # 1: tensor-core sweep in the stepwise loop ...
+    monkeypatch.setenv("PMP_PERSISTENT_TC", str(tc))          # ... and in the persistent kernel
     monkeypatch.setenv("PMP_PERSISTENT", str(persistent))     # 1: one cooperative kernel for the whole chain; 0: CUDA-graph replay of sweep + acceptance
     monkeypatch.setenv("PMP_GRAPH_ITERS", "8")
     iters, seed = 13, 77
@@ -169,8 +170,9 @@ def test_device_resident_chain_replays_in_oracle(tree, b, depth, algo, draw, fla
         c.close()
 
 
-@pytest.mark.parametrize("n,P", [(500, 4), (500, 1024), (64, 16), (100000, 4), (5000, 3000)])
-def test_loop_structures_agree(n, P, monkeypatch):
+@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("n,P", [(500, 4), (500, 1024), (64, 16), (100000, 4), (5000, 3000), (100000, 1024), (20000, 300)])
+def test_loop_structures_agree(n, P, tc, monkeypatch):
     """The persistent cooperative kernel and the CUDA-graph replay of sweep + acceptance are two schedules of the same
     arithmetic: identical states, accepted indices and log-weight bits after the same number of iterations — also when
     there are fewer (tile, chunk) units than sweep CTAs (n = 500: 8 chunks) or more nodes than one CTA's tile."""
@@ -178,6 +180,7 @@ def test_loop_structures_agree(n, P, monkeypatch):
     L = _L()
     x, y = synthetic_linear(n, seed=9)
     out = []
+    monkeypatch.setenv("PMP_SWEEP_TC", str(tc)); monkeypatch.setenv("PMP_PERSISTENT_TC", str(tc))      # same sweep arithmetic in both loops
     for persistent in (1, 0):
         monkeypatch.setenv("PMP_PERSISTENT", str(persistent))
         c = pm.Context(0)
