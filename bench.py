@@ -35,6 +35,9 @@ METRIC = "proposal-evals/sec"
 UNIT = "proposal-evals/s"
 # README.md:44 of the reference (V100): MP, n=100000, P=1024: 33473.53 us kernel + 1099.258 us host/copy per iteration
 BASELINE_EVALS_PER_S = 1024 / ((33473.53 + 1099.258) * 1e-6)
+# dram__bytes_read.sum + dram__bytes_write.sum of one chain_persistent_kernel launch, ncu --set full (profiles/r1b_chain_persistent_ncu_full_summary.txt,
+# a 50-iteration launch: the dataset is read from HBM once per launch and then lives in shared memory)
+NCU_DRAM_BYTES_PER_LAUNCH = 914944 + 2304
 
 
 def synthetic(n, seed=0):
@@ -219,7 +222,7 @@ def main():
     else:
         kernel, kernel_us, launch_flops = "sweep_linear_kernel<4,true>", sweep_ms * 1e3, flops_per_iter
     achieved = launch_flops / (kernel_us * 1e-6) / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH if persistent else None,
                 "peak_source": "measured in this run by pmp_fp32_peak (FFMA/FFMA2 microbenchmark); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "note": "the sweep is bound by FP32 issue (3 lane-ops per node-point pair), not by HBM (0.8 MB, L2/shared-memory resident) nor by the tensor pipe; see DESIGN.md 4",
                 "kernel": kernel, "kernel_us": kernel_us, "flops_per_launch": launch_flops,

@@ -17,15 +17,16 @@
 //     image of the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, K-adjacent cores 128 B apart,
 //     row groups 256 B apart), so staging is a plain 16-byte-vector copy and consecutive chunks form one N <= 256 operand;
 //   * the node operand (32 B per node) is rebuilt from the published nodes at the start of every sweep by all threads;
-//   * one thread issues tcgen05.mma into two 256-column TMEM halves (double buffer, mbarrier full/empty hand-off);
-//     eight epilogue warps (two per TMEM lane quarter, two 64-point chunks each) read the residuals with tcgen05.ld
-//     and run acc = fma(r, r, acc) as packed fma.rn.f32x2; one float32 partial per (node, chunk) in a fixed order, then
-//     the same binary64 scale + round-to-integer + integer adds as the FMA path, so the sum is still bit-identical for
-//     any CTA order, grid size, loop structure and number of GPUs.
+//   * the CTA runs four independent pipelines ("sets"): set j owns TMEM columns [128j, 128j+128) as two 64-column stages,
+//     the units v = j, j+4, ... of the CTA's walk, one issuer warp (one N = 64 UMMA per unit, mbarrier full/empty hand-off)
+//     and four epilogue warps, one per TMEM lane quarter, that read the residuals with tcgen05.ld and run
+//     acc = fma(r, r, acc) as packed fma.rn.f32x2; one float32 partial per (node, chunk) in a fixed order, then the same
+//     binary64 scale + round-to-integer + integer adds as the FMA path, so the sum is still bit-identical for any CTA
+//     order, grid size, loop structure and number of GPUs.
 // Units of work are (chunk, 128-node tile) pairs in chunk-major order cut into gridDim.x equal contiguous ranges; a CTA
-// keeps its chunks resident in shared memory and walks them tile by tile, four units per TMEM half.
-// Bounds: tensor pipe 2*128*16 flop per (tile, point) — 43 % busy at the epilogue's best rate; the epilogue is bound by
-// FP32 issue (1 lane-op per pair) and TMEM read bandwidth (measured 440 B/clk/SM with the FMA, scripts/micro/micro3.cu).
+// keeps its chunks resident in shared memory and walks them tile by tile.
+// Bounds and what was measured: the epilogue's ceiling is TMEM read + FP32 issue (440 B/clk/SM with the FMA,
+// scripts/micro/micro3.cu); in practice the per-unit instruction overhead and UMMA latency x TMEM capacity bind first.
 #pragma once
 #include <cuda_bf16.h>
 #ifndef PMP_TC_ABL
