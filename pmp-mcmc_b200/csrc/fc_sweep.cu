@@ -19,6 +19,18 @@
 //   NLL         bias, log-softmax over the 10 classes, pick the label, sum over rows into a 2^-32 fixed-point integer
 //               (exact, order-free: identical bits for any CTA order and any data sharding).
 // Every mbarrier wait is bounded (trap instead of hang).
+//
+// v2 (default; PMP_FC_V1=1 selects the kernel above): fc_gemm2_kernel.  The v1 kernel is limited by operand traffic, not by the
+// tensor pipe: [Ah|Ah|Al].[Bh|Bl|Bh] streams six tiles through L2 -> shared memory for every three MMAs, and a one-tile CTA
+// cannot overlap its epilogue with anything.  v2 changes the dataflow, not the arithmetic:
+//   * operands are stored once as [h | l]; a pipeline stage holds the four tiles Ah, Al, Bh, Bl of one 64-wide K block and
+//     the issuer runs the three products Ah.Bh, Ah.Bl, Al.Bh from them (4 tile loads per 3 MMAs instead of 6);
+//   * CTA pairs (cluster of 2, tcgen05.mma.cta_group::2): one 256 x BN accumulator tile per pair, each CTA loads its own 128
+//     data rows and HALF of the weight rows, so L2 -> SM bytes per flop drop 2.25x against v1;
+//   * persistent CTAs with a static tile schedule (node fastest: the CTAs working on one data-row block run together and
+//     the block is read from HBM once), two accumulator stages in TMEM: the epilogue of tile i runs under the MMAs of tile i+1;
+//   * the last layer (128 -> 10) is folded into layer 3's epilogue in fp32 on the CUDA cores (its activations are already in
+//     TMEM), followed by the log-softmax/NLL and the fixed-point row sum: one kernel and one activation round trip less.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -48,9 +60,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > 200000000u) __trap();       // a protocol bug must fail loudly, never hang the GPU
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
+    for (unsigned spins = 1; !mbar_try_wait(bar, parity); ++spins)
+        if ((spins & 1023u) == 0 && global_ns() - t0 > 4000000000ull) __trap();   // 4 s: a protocol bug must fail loudly, never hang the GPU
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -220,6 +235,245 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) fc_gemm_kernel(const __grid_c
     (void)s_red;
 }
 
+
+// ===================================================== v2 ================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of a pair load into their own shared memory; the transaction bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once) on the mbarrier at this offset in BOTH CTAs of the pair when the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1 };
+
+struct Gemm2Args {
+    int M;                    // data rows of this shard
+    int Kpad;                 // padded K (multiple of 64); operands are [.., 2*Kpad] = [h | l]
+    int a_shared;             // 1: A has no node axis (layer 1: the data are the same for every node)
+    int n_total;              // N of the layer
+    int nb;                   // nodes in this batch
+    const float* bias;        // [nb, bias_stride] (already offset to this layer)
+    int bias_stride;
+    __nv_bfloat16* out;       // RELU_SPLIT: next layer's A' [nb, M, 2*n_total]
+    const float* theta;       // L4_NLL: node parameters (float32, torch order) of the first node of the batch
+    long long theta_stride;
+    const int* labels;        // L4_NLL: [M]
+    unsigned long long* loss; // L4_NLL: [nb] fixed-point sums
+};
+
+template <int BN, int EPI, int NSTAGE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int BH = BN / 2;                                   // weight rows each CTA of the pair loads
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BH * BK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;       // Ah, Al, Bh, Bl
+    constexpr int TMEM_COLS = 2 * BN;                            // two accumulator stages
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_w4[EPI == EPI2_L4_NLL ? H3 * 12 : 4];
+    __shared__ float s_b3[EPI == EPI2_L4_NLL ? H3 : 1], s_b4[EPI == EPI2_L4_NLL ? NCLS_PAD : 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int nblk_n = g.n_total / BN;
+    const int inner = nblk_n * g.nb;                             // tiles that share one block of data rows: scheduled back to back
+    const int total = ((g.M + 2 * BM - 1) / (2 * BM)) * inner;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int num_k = g.Kpad / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }   // 4 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                             // the same warp of BOTH CTAs allocates (and later frees) jointly
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                          // barriers of both CTAs initialised before any remote arrive
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                         // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0;
+            for (int t = pair; t < total; t += npairs) {
+                const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
+                const int row0 = m_blk * 2 * BM + (int)rank * BM, col0 = n_blk * BN + (int)rank * BH;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, round = it / NSTAGE;
+                    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                    tma_load_3d_2sm(st, &tmA, lbar, kb * BK, row0, g.a_shared ? 0 : batch);
+                    tma_load_3d_2sm(st + A_BYTES, &tmA, lbar, g.Kpad + kb * BK, row0, g.a_shared ? 0 : batch);
+                    tma_load_3d_2sm(st + 2 * A_BYTES, &tmB, lbar, kb * BK, col0, batch);
+                    tma_load_3d_2sm(st + 2 * A_BYTES + B_BYTES, &tmB, lbar, g.Kpad + kb * BK, col0, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {                            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            uint32_t it = 0; int j = 0;
+            for (int t = pair; t < total; t += npairs, ++j) {
+                const int acc = j & 1, use = j >> 1;
+                if (use > 0) { mbar_wait(&tempty_bar[acc], (use - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, round = it / NSTAGE;
+                    mbar_wait(&full_bar[s], round & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    const uint64_t ah = umma_desc_sw128(st), al = umma_desc_sw128(st + A_BYTES);
+                    const uint64_t bh = umma_desc_sw128(st + 2 * A_BYTES), bl = umma_desc_sw128(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {      // +32 B along K inside the 128-byte swizzle atom = +2 in the address field
+                        umma_bf16_2sm(d_tmem, ah + 2ull * k, bh + 2ull * k, idesc, (kb | k) != 0);
+                        umma_bf16_2sm(d_tmem, ah + 2ull * k, bl + 2ull * k, idesc, 1);
+                        umma_bf16_2sm(d_tmem, al + 2ull * k, bh + 2ull * k, idesc, 1);
+                    }
+                    umma_commit_2sm(&empty_bar[s]);              // frees this stage in both CTAs when the MMAs retire
+                }
+                umma_commit_2sm(&tfull_bar[acc]);                // accumulator stage complete, seen by both CTAs' epilogue warps
+            }
+        }
+    } else {                                                     // ===== epilogue warps 2..5 (both CTAs) =====
+        const int quarter = warp & 3;                            // TMEM lanes [32q, 32q+32) are the only ones this warp may read
+        const int et = (warp - 2) * 32 + lane;                   // 0..127
+        const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+        int j = 0;
+        for (int t = pair; t < total; t += npairs, ++j) {
+            const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
+            const int acc = j & 1, use = j >> 1;
+            const int row = m_blk * 2 * BM + (int)rank * BM + quarter * 32 + lane;
+            if (EPI == EPI2_L4_NLL) {                            // this node's last layer -> shared memory (transposed, 12-float rows)
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // everybody is done with the previous tile's copy
+                const float* th = g.theta + (long long)batch * g.theta_stride;
+                for (int i = et; i < NCLS * H3; i += 128) { const int c = i / H3, jj = i - c * H3; s_w4[jj * 12 + c] = __ldg(th + OFF_W4 + i); }
+                s_b3[et] = __ldg(g.bias + (long long)batch * g.bias_stride + et);
+                if (et < NCLS) s_b4[et] = __ldg(th + OFF_B4 + et);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&tfull_bar[acc], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            if (EPI == EPI2_RELU_SPLIT) {
+                const float* bias = g.bias + (long long)batch * g.bias_stride + n_blk * BN;
+                const long long ldo = 2ll * g.n_total;
+                __nv_bfloat16* orow = g.out + ((long long)batch * g.M + row) * ldo + n_blk * BN;
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+                    uint32_t hp[16], lp[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a0 = fmaxf(__uint_as_float(v[2 * i]) + __ldg(bias + cc * 32 + 2 * i), 0.f);
+                        float a1 = fmaxf(__uint_as_float(v[2 * i + 1]) + __ldg(bias + cc * 32 + 2 * i + 1), 0.f);
+                        __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+                        __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
+                        hp[i] = pack_bf16x2(h0, h1); lp[i] = pack_bf16x2(l0, l1);
+                    }
+                    if (row < g.M) {
+                        uint4* d0 = reinterpret_cast<uint4*>(orow + cc * 32);
+                        uint4* d1 = reinterpret_cast<uint4*>(orow + g.n_total + cc * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            d0[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+                            d1[q] = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+                        }
+                    }
+                }
+            } else {
+                float z[NCLS];
+#pragma unroll
+                for (int c = 0; c < NCLS; ++c) z[c] = s_b4[c];
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int jj = cc * 32 + i;
+                        const float a = fmaxf(__uint_as_float(v[i]) + s_b3[jj], 0.f);
+                        const float4 w0 = *reinterpret_cast<const float4*>(&s_w4[jj * 12]);
+                        const float4 w1 = *reinterpret_cast<const float4*>(&s_w4[jj * 12 + 4]);
+                        const float2 w2 = *reinterpret_cast<const float2*>(&s_w4[jj * 12 + 8]);
+                        z[0] = fmaf(a, w0.x, z[0]); z[1] = fmaf(a, w0.y, z[1]); z[2] = fmaf(a, w0.z, z[2]); z[3] = fmaf(a, w0.w, z[3]);
+                        z[4] = fmaf(a, w1.x, z[4]); z[5] = fmaf(a, w1.y, z[5]); z[6] = fmaf(a, w1.z, z[6]); z[7] = fmaf(a, w1.w, z[7]);
+                        z[8] = fmaf(a, w2.x, z[8]); z[9] = fmaf(a, w2.y, z[9]);
+                    }
+                }
+                float mx = z[0];
+#pragma unroll
+                for (int c = 1; c < NCLS; ++c) mx = fmaxf(mx, z[c]);
+                float se = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCLS; ++c) se += expf(z[c] - mx);
+                float nll = 0.f;
+                if (row < g.M) {
+                    const int lab = g.labels[row];
+                    float zl = z[0];
+#pragma unroll
+                    for (int c = 1; c < NCLS; ++c) zl = (lab == c) ? z[c] : zl;
+                    nll = (mx + logf(se)) - zl;
+                }
+                // per-row NLL -> 2^-32 fixed point; everything after this line is integer (exact, order-free)
+                long long q = (row < g.M) ? __double2ll_rn((double)nll * 4294967296.0) : 0ll;
+                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                if (lane == 0 && q != 0) atomicAdd(g.loss + batch, (unsigned long long)q);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);   // this accumulator stage may be overwritten
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                          // nobody leaves (or frees TMEM) while the peer can still signal it
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+// v f32 [rows, K] (node-strided) -> bf16 [nb, rows_pad, 2*Kpad] = [h | l], zero padded
+__global__ void split2_kernel(const float* __restrict__ src, long long node_stride, long long off, int rows, int K, int rows_pad, int Kpad,
+                              __nv_bfloat16* __restrict__ out, int nb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long per = (long long)rows_pad * Kpad;
+    if (i >= per * nb) return;
+    int b = (int)(i / per); long long rem = i - b * per;
+    int r = (int)(rem / Kpad), c = (int)(rem - (long long)r * Kpad);
+    float v = (r < rows && c < K) ? src[b * node_stride + off + (long long)r * K + c] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+    __nv_bfloat16* o = out + ((long long)b * rows_pad + r) * (2ll * Kpad);
+    o[c] = h; o[Kpad + c] = l;
+}
+
 // X f32 [n, 784] → X' bf16 [n, 3*832] = [h | h | l], zero padded
 __global__ void split_x_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ out, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,6 +558,7 @@ struct FcState {
     unsigned long long* loss = nullptr;   // [P]
     float* s1 = nullptr; double* dj2 = nullptr; double* dot = nullptr;
     CUtensorMap tmX, tmW1, tmA2, tmW2, tmA3, tmW3, tmA4, tmW4;
+    int version = 2;                   // 2: fc_gemm2_kernel ([h | l] operands, CTA pairs, persistent); 1: fc_gemm_kernel
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -331,6 +586,21 @@ static int make_map(CUtensorMap* m, void* base, long long K3, long long rows, lo
 }
 
 template <int BN, int EPI> static size_t gemm_smem() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024; }
+
+template <int BN, int EPI, int NSTAGE>
+static int launch_gemm2(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, const Gemm2Args& g) {
+    constexpr size_t smem = (size_t)NSTAGE * (2 * BM * BK * 2 + 2 * (BN / 2) * BK * 2) + 1024;
+    static bool attr = false;
+    if (!attr) { PMP_CUDA(cudaFuncSetAttribute(fc_gemm2_kernel<BN, EPI, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const long long tiles = (long long)((g.M + 2 * BM - 1) / (2 * BM)) * (g.n_total / BN) * g.nb;
+    long long pairs = c->sm_count / 2;
+    if (pairs > tiles) pairs = tiles;
+    if (pairs < 1) pairs = 1;
+    fc_gemm2_kernel<BN, EPI, NSTAGE><<<dim3((unsigned)(2 * pairs)), GEMM_THREADS, smem, c->stream>>>(a, b, g);   // cluster dims (2,1,1) are a kernel attribute
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
 
 template <int BN, int EPI>
 static int launch_gemm(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int n_total, int nb) {
@@ -373,20 +643,39 @@ int pmp_set_data_fc(pmp_ctx* c, const float* X, const int64_t* labels, int64_t n
     s->n_local = n_local; s->n_global = n_global;
     s->nb = getenv("PMP_FC_BATCH") ? atoi(getenv("PMP_FC_BATCH")) : 8;
     if (s->nb < 1) s->nb = 1;
+    s->version = (getenv("PMP_FC_V1") && atoi(getenv("PMP_FC_V1"))) ? 1 : 2;
+    const int planes = s->version == 2 ? 2 : 3;            // [h | l] or [h | h | l]
     float* d_x32 = nullptr;
     std::vector<int> lab32((size_t)n_local);
     for (int64_t i = 0; i < n_local; ++i) { PMP_REQUIRE(labels[i] >= 0 && labels[i] < NCLS, "label %lld out of range at row %lld", (long long)labels[i], (long long)i); lab32[i] = (int)labels[i]; }
     PMP_CUDA(cudaMalloc((void**)&d_x32, (size_t)n_local * D_IN * sizeof(float)));
-    PMP_CUDA(cudaMalloc((void**)&s->xs, (size_t)n_local * 3 * D_IN_PAD * sizeof(__nv_bfloat16)));
+    PMP_CUDA(cudaMalloc((void**)&s->xs, (size_t)n_local * planes * D_IN_PAD * sizeof(__nv_bfloat16)));
     PMP_CUDA(cudaMalloc((void**)&s->labels, (size_t)n_local * sizeof(int)));
     PMP_CUDA(cudaMemcpyAsync(d_x32, X, (size_t)n_local * D_IN * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     PMP_CUDA(cudaMemcpyAsync(s->labels, lab32.data(), (size_t)n_local * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     long long tot = n_local * D_IN_PAD;
-    split_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_x32, s->xs, n_local);
+    if (s->version == 2) split2_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_x32, 0, 0, (int)n_local, D_IN, (int)n_local, D_IN_PAD, s->xs, 1);
+    else split_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_x32, s->xs, n_local);
     c->launches++;
     PMP_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_x32);
     const int nb = s->nb;
+    if (s->version == 2) {
+        PMP_CUDA(cudaMalloc((void**)&s->w1, (size_t)nb * H1 * 2 * D_IN_PAD * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->w2, (size_t)nb * H2 * 2 * H1 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->w3, (size_t)nb * H3 * 2 * H2 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->bias, (size_t)nb * (H1 + H2 + H3 + NCLS_PAD) * sizeof(float)));
+        PMP_CUDA(cudaMalloc((void**)&s->a2, (size_t)nb * n_local * 2 * H1 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->a3, (size_t)nb * n_local * 2 * H2 * 2));
+        int rc2;
+        if ((rc2 = make_map(&s->tmX, s->xs, 2 * D_IN_PAD, n_local, 1, BM))) return rc2;
+        if ((rc2 = make_map(&s->tmW1, s->w1, 2 * D_IN_PAD, H1, nb, 128))) return rc2;     // each CTA of a pair loads half of the 256 weight rows
+        if ((rc2 = make_map(&s->tmA2, s->a2, 2 * H1, n_local, nb, BM))) return rc2;
+        if ((rc2 = make_map(&s->tmW2, s->w2, 2 * H1, H2, nb, 128))) return rc2;
+        if ((rc2 = make_map(&s->tmA3, s->a3, 2 * H2, n_local, nb, BM))) return rc2;
+        if ((rc2 = make_map(&s->tmW3, s->w3, 2 * H2, H3, nb, 64))) return rc2;
+        return PMP_OK;
+    }
     PMP_CUDA(cudaMalloc((void**)&s->w1, (size_t)nb * H1 * 3 * D_IN_PAD * 2));
     PMP_CUDA(cudaMalloc((void**)&s->w2, (size_t)nb * H2 * 3 * H1 * 2));
     PMP_CUDA(cudaMalloc((void**)&s->w3, (size_t)nb * H3 * 3 * H2 * 2));
@@ -421,6 +710,21 @@ int pmp_fc_loglik(pmp_ctx* c) {
         const int nb = (P - p0) < s->nb ? (P - p0) : s->nb;
         const float* th = c->d_props + (long long)p0 * THETA_DIM;
         long long t;
+        if (s->version == 2) {
+            t = (long long)nb * H1 * D_IN_PAD;   split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, OFF_W1, H1, D_IN, H1, D_IN_PAD, s->w1, nb);
+            t = (long long)nb * H2 * H1;         split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, OFF_W2, H2, H1, H2, H1, s->w2, nb);
+            t = (long long)nb * H3 * H2;         split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, OFF_W3, H3, H2, H3, H2, s->w3, nb);
+            t = (long long)nb * bias_stride;     gather_bias_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, s->bias, nb);
+            c->launches += 4;
+            PMP_CUDA(cudaGetLastError());
+            Gemm2Args g1{M, D_IN_PAD, 1, H1, nb, s->bias, bias_stride, s->a2, nullptr, 0, nullptr, nullptr};
+            if ((rc = launch_gemm2<256, EPI2_RELU_SPLIT, 3>(c, s->tmX, s->tmW1, g1))) return rc;
+            Gemm2Args g2{M, H1, 0, H2, nb, s->bias + H1, bias_stride, s->a3, nullptr, 0, nullptr, nullptr};
+            if ((rc = launch_gemm2<256, EPI2_RELU_SPLIT, 3>(c, s->tmA2, s->tmW2, g2))) return rc;
+            Gemm2Args g3{M, H2, 0, H3, nb, s->bias + H1 + H2, bias_stride, nullptr, th, THETA_DIM, s->labels, s->loss + p0};
+            if ((rc = launch_gemm2<128, EPI2_L4_NLL, 4>(c, s->tmA3, s->tmW3, g3))) return rc;
+            continue;
+        }
         t = (long long)nb * H1 * D_IN_PAD;   split_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, OFF_W1, H1, D_IN, H1, D_IN_PAD, s->w1, nb);
         t = (long long)nb * H2 * H1;         split_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, OFF_W2, H2, H1, H2, H1, s->w2, nb);
         t = (long long)nb * H3 * H2;         split_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, OFF_W3, H3, H2, H3, H2, s->w3, nb);
