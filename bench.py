@@ -3,8 +3,14 @@
 P = 1024 candidate states per iteration, n = 100 000 data points (BASELINE.json metric; the reference's
 `100000_MP.cu` time-analysis shape: flat proposals, CUDA draw rule, SCALE 1000, alpha 0.01, theta0 = (1,1,1)).
 
-A "step" is one block of ITERS_PER_STEP chain iterations run device-resident (pmp_run).  Between steps L2 is flushed
-(256 MB memset); inside a step the 0.8 MB dataset is re-read from L2 by design — that is what a chain does.
+A "step" is one block of ITERS_PER_STEP iterations of every chain, run device-resident.  Between steps L2 is flushed
+(256 MB memset); inside a step the 0.8 MB dataset is re-read from L2 / shared memory by design — that is what a chain does.
+
+Single GPU: the workload is CHAINS (default 4) INDEPENDENT chains of that shape co-scheduled in one cooperative kernel
+(pmp_run_multi): one chain alone is a dependency loop that leaves the sweep SMs idle while it is being accepted, and
+independent repeats are how the reference's experiments are run.  Each chain's trace is bit-identical to the chain run alone
+(tests/test_gpu_multichain.py); `value` counts the proposal evaluations of all chains, `single_chain` in the same JSON line
+is one chain alone (pmp_run), so both the throughput and the latency-bound figure are on record.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -29,15 +35,18 @@ sys.path.insert(0, ROOT)
 P_NODES = 1024
 N_DATA = 100000
 ITERS_PER_STEP = 1000
+CHAINS = 4
 SCALE = 1000.0
 ALPHA = 0.01
 METRIC = "proposal-evals/sec"
 UNIT = "proposal-evals/s"
 # README.md:44 of the reference (V100): MP, n=100000, P=1024: 33473.53 us kernel + 1099.258 us host/copy per iteration
 BASELINE_EVALS_PER_S = 1024 / ((33473.53 + 1099.258) * 1e-6)
-# dram__bytes_read.sum + dram__bytes_write.sum of one chain_persistent_kernel launch, ncu --set full (profiles/r1b_chain_persistent_ncu_full_summary.txt,
-# a 50-iteration launch: the dataset is read from HBM once per launch and then lives in shared memory)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full: the dataset is read from HBM once per launch and
+# then lives in shared memory.  Single chain: profiles/r1b_chain_persistent_ncu_full_summary.txt (50-iteration launch);
+# co-scheduled chains: profiles/r1c_chain_persistent_multi_ncu_full_summary.txt (4 chains x 50 iterations).
 NCU_DRAM_BYTES_PER_LAUNCH = 914944 + 2304
+NCU_DRAM_BYTES_PER_LAUNCH_MULTI = None
 
 
 def synthetic(n, seed=0):
@@ -91,6 +100,29 @@ def cpu_port_evals_per_s(x, y, n_evals, threads=None):
     return n_evals / dt, torch.get_num_threads(), dt
 
 
+def reference_cuda_kernel(x, y, P):
+    """The reference's own log_likelihood_kernel (100000_MP.cu:10-36, compiled from its source into oracle/_ref by oracle/Makefile)
+    on this GPU: one launch evaluates P proposals.  Reported beside the CPU baseline; None when oracle/_ref was not built."""
+    import ctypes
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_mp_100000.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        lib = ctypes.CDLL(path)
+        lib.ref_set_data.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.ref_loglik.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+        rng = np.random.default_rng(1)
+        nets = np.ascontiguousarray((np.array([1, 1, 1], np.float32) + ALPHA * rng.standard_normal((P, 3))).astype(np.float32))
+        out = np.empty(P, np.float32)
+        ms = ctypes.c_float()
+        if lib.ref_set_data(x.ctypes.data, y.ctypes.data, len(x)) != 0 or lib.ref_loglik(nets.ctypes.data, P, out.ctypes.data, 5, ctypes.byref(ms)) != 0:
+            return None
+        return {"kernel_us": ms.value * 1e3, "value": P / (ms.value * 1e-3), "unit": UNIT,
+                "what": "reference log_likelihood_kernel<<<ceil(P/256),256>>> recompiled for sm_100a, P=%d, n=%d, kernel time only (no host loop, no copies), mean of 5 launches" % (P, len(x))}
+    except OSError:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -122,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--iters-per-step", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--weak", action="store_true", help="n = 100000 per GPU instead of 100000 in total")
+    ap.add_argument("--chains", type=int, default=CHAINS, help="independent chains co-scheduled on one GPU (1: a single chain with pmp_run)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -141,16 +174,45 @@ def main():
     x, y = synthetic(n_global)
     xp, yp = torch.from_numpy(x).pin_memory().numpy(), torch.from_numpy(y).pin_memory().numpy()     # pinned host buffers for the e2e arm
 
-    ctx.configure(L.TREE_FLAT, b=P_NODES, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=ALPHA, scale=SCALE)
+    # N = 1: the chains share one cooperative kernel.  N > 1: every chain's data are sharded over the ranks and the chains run on
+    # separate streams / NCCL communicators, so one chain's all-reduce and acceptance overlap the other chains' sweeps.
+    chains = max(1, min(4, args.chains))
+
+    def configure(c):
+        c.configure(L.TREE_FLAT, b=P_NODES, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=ALPHA, scale=SCALE)
+
+    configure(ctx)
     lo, hi = pdist.set_data_linear_sharded(ctx, xp, yp)
-    ctx.set_state([1, 1, 1])
-    ctx.seed(2024, 0)
+    ctxs = [ctx]
+    for k in range(1, chains):
+        c = pdist.create_context(local)
+        configure(c)
+        c.share_data_from(ctx)
+        ctxs.append(c)
+
+    def reset(seed0):
+        for k, c in enumerate(ctxs):
+            c.set_state([1, 1, 1]); c.seed(seed0 + k, 0)
+
+    def run_step(timed):
+        if chains == 1:
+            if timed:
+                return ctx.run_timed(iters)[0]
+            ctx.run(iters)
+            return None
+        if timed:
+            return L.run_multi_timed(ctxs, iters)
+        L.run_multi(ctxs, iters)
+        return None
+
+    reset(2024)
 
     def barrier():
         if world > 1:
             td.barrier()
         torch.cuda.synchronize()
-        ctx.sync()
+        for c in ctxs:
+            c.sync()
 
     def max_over_ranks(v):
         if world == 1:
@@ -161,42 +223,61 @@ def main():
 
     # ---- device-resident arm: inputs already in HBM, CUDA events on the ctx stream, max over ranks -------------------
     for _ in range(args.warmup):
-        ctx.l2_flush(); ctx.run(iters)
+        ctx.l2_flush(); run_step(False)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = ctx.launch_count()
+    launches0 = sum(c.launch_count() for c in ctxs)
     step_ms = []
     for _ in range(args.steps):
         ctx.l2_flush()
         barrier()
-        ms, _ = ctx.run_timed(iters)
-        step_ms.append(max_over_ranks(ms))
+        step_ms.append(max_over_ranks(run_step(True)))
     barrier()
-    launches = ctx.launch_count() - launches0
+    launches = sum(c.launch_count() for c in ctxs) - launches0
     total_s = sum(step_ms) * 1e-3
     clocks = sampler.summary()
-    iters_per_s = args.steps * iters / total_s
+    iters_per_s = args.steps * iters * chains / total_s            # chain iterations per second, all chains
     value = iters_per_s * P_NODES
+
+    # ---- one chain alone (pmp_run): the latency-bound figure -------------------------------------------------------------
+    single = None
+    if chains > 1:
+        ctx.set_state([1, 1, 1]); ctx.seed(2024, 0)
+        ctx.l2_flush(); ctx.run(iters)
+        ms1 = []
+        for _ in range(3):
+            ctx.l2_flush(); ctx.sync()
+            ms1.append(ctx.run_timed(iters)[0])
+        us1 = float(np.mean(ms1)) * 1e3 / iters
+        single = {"value": P_NODES * 1e6 / us1, "unit": UNIT, "iters_per_sec": 1e6 / us1, "us_per_iter": us1,
+                  "what": "one chain alone, chain_persistent_kernel via pmp_run, 3 steps of %d iterations" % iters}
 
     # ---- end-to-end arm: host buffers in, trace out, through the C-ABI the Python samplers call ----------------------
     e2e_s = []
+    for c in ctxs:
+        c.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS)
+    outs = [c.trace_buffers(pinned=True) for c in ctxs]            # page-locked host buffers the traces are copied into
     for s in range(2 + args.steps):
         barrier()
         t0 = time.perf_counter()
-        pdist.set_data_linear_sharded(ctx, xp, yp)                 # H2D: this rank's shard of x and y
-        ctx.set_state([1, 1, 1]); ctx.seed(7, 0)
-        ctx.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS)
-        ctx.run(iters)
-        tr = ctx.read_trace()                                       # D2H: states [iters,3] f32, accepted index [iters] i32, the P resampled indices [iters,P] i32
+        pdist.set_data_linear_sharded(ctx, xp, yp)                 # H2D: this rank's shard of x and y (the other chains alias it)
+        for c in ctxs[1:]:
+            c.share_data_from(ctx)
+        reset(7)
+        for c in ctxs:
+            c.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS)
+        run_step(False)
+        trs = [c.read_trace(out=o) for c, o in zip(ctxs, outs)]                        # D2H per chain: states [iters,3] f32, accepted index [iters] i32, the P resampled indices [iters,P] i32
         dt = max_over_ranks(time.perf_counter() - t0)
-        assert tr["n"] == iters
+        assert all(tr["n"] == iters for tr in trs)
         if s >= 2:
             e2e_s.append(dt)
-    e2e_value = args.steps * iters * P_NODES / sum(e2e_s)
-    h2d = int((hi - lo) * 8 + 12)
-    d2h = int(iters * (16 + 4 * P_NODES))
-    ctx.trace_config(0, 0)
+    e2e_value = args.steps * iters * chains * P_NODES / sum(e2e_s)
+    h2d = int((hi - lo) * 8 + 12 * chains)
+    d2h = int(chains * iters * (16 + 4 * P_NODES))
+    for c in ctxs:
+        c.trace_config(0, 0)
 
     # ---- roofline of the dominant kernel: algorithmic flops / average launch duration ----------------------------------
     # Single GPU: the whole chain is ONE cooperative launch (chain_persistent_kernel: 147 sweep CTAs + 1 acceptance CTA), so
@@ -216,13 +297,18 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     persistent = world == 1 and os.environ.get("PMP_PERSISTENT", "1") != "0"
-    iter_s = total_s / (args.steps * iters)
-    if persistent:
+    iter_s = total_s / (args.steps * iters * chains)               # seconds per chain iteration
+    traffic = None
+    if chains > 1 and world == 1:
+        kernel, kernel_us, launch_flops = "chain_persistent_multi_kernel<MP> (%d chains, one launch per step)" % chains, iter_s * 1e6 * iters * chains, flops_per_iter * iters * chains
+        traffic = NCU_DRAM_BYTES_PER_LAUNCH_MULTI
+    elif persistent:
         kernel, kernel_us, launch_flops = "chain_persistent_kernel<MP> (one launch per step)", iter_s * 1e6 * iters, flops_per_iter * iters
+        traffic = NCU_DRAM_BYTES_PER_LAUNCH
     else:
         kernel, kernel_us, launch_flops = "sweep_linear_kernel<4,true>", sweep_ms * 1e3, flops_per_iter
     achieved = launch_flops / (kernel_us * 1e-6) / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH if persistent else None,
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured in this run by pmp_fp32_peak (FFMA/FFMA2 microbenchmark); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "note": "the sweep is bound by FP32 issue (3 lane-ops per node-point pair), not by HBM (0.8 MB, L2/shared-memory resident) nor by the tensor pipe; see DESIGN.md 4",
                 "kernel": kernel, "kernel_us": kernel_us, "flops_per_launch": launch_flops,
@@ -237,21 +323,24 @@ def main():
         if world == 1:
             v, cores, dt = cpu_port_evals_per_s(x, y, 40960)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "40960 proposal-evaluations at n=100000 (40 sweeps of P=1024) with the lb.py per-proposal torch loop, %.1f s" % dt}
+                   "sample": "40960 proposal-evaluations at n=100000 (40 sweeps of P=1024) with the lb.py per-proposal torch loop, %.1f s" % dt,
+                   "reference_cuda_kernel_same_gpu": reference_cuda_kernel(x, y, P_NODES)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32", "data": "synthetic",
-                "iters_per_sec": iters_per_s, "us_per_iter": 1e6 / iters_per_s,
-                "config": {"workload": "simple_net linear-Gaussian multi-proposal MCMC (100000_MP.cu shape): P=1024 nodes, n=%d points, flat proposals alpha=0.01, SCALE=1000, CUDA draw rule" % n_global,
-                           "P": P_NODES, "n": n_global, "iters_per_step": iters, "device": info["name"],
+                "iters_per_sec": iters_per_s, "us_per_iter": 1e6 / iters_per_s, "single_chain": single,
+                "config": {"workload": "simple_net linear-Gaussian multi-proposal MCMC (100000_MP.cu shape): P=1024 nodes, n=%d points, flat proposals alpha=0.01, SCALE=1000, CUDA draw rule; "
+                                       "%d independent chain(s) per GPU%s" % (n_global, chains, (" co-scheduled in one cooperative kernel (pmp_run_multi)" if world == 1 else " on separate streams and NCCL communicators, data sharded over the ranks (pmp_run_multi)") + "; iters_per_sec and value count all chains" if chains > 1 else ""),
+                           "P": P_NODES, "n": n_global, "chains": chains, "iters_per_step": iters, "device": info["name"],
                            "l2": "flushed (256 MB memset) between steps; inside a step the dataset is re-read from L2 by design",
                            "baseline": "reference README.md:44, V100: (33473.53 + 1099.258) us per iteration at P=1024, n=100000"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "what": "set_data (pinned host x,y) + set_state + %d iterations + read_trace (states, accepted indices and all P resampled indices per iteration) per step, wall clock" % iters},
+                        "what": "set_data (pinned host x,y) + per chain: set_state, seed, %d iterations, read_trace (states, accepted indices and all P resampled indices per iteration); %d chain(s) per step, wall clock" % (iters, chains)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
-    ctx.close()
+    for c in reversed(ctxs):
+        c.close()
     if world > 1:
         td.destroy_process_group()
 

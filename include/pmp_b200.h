@@ -156,6 +156,17 @@ int pmp_read_logweights(pmp_ctx* ctx, double* out, int64_t count);   /* A_p of t
 int pmp_trace_config(pmp_ctx* ctx, int64_t max_iters, uint32_t what);
 int pmp_run(pmp_ctx* ctx, int64_t iters, int sync);
 int pmp_sync(pmp_ctx* ctx);
+
+/* Co-scheduled chains.  A single chain is a dependency loop (sweep on all SMs → acceptance on one → next sweep), so the sweep
+ * SMs idle while their chain is being accepted.  pmp_run_multi runs n_ctx (<= 4) INDEPENDENT chains — one pmp_ctx each: own
+ * state, Philox key, trace — in one cooperative kernel, sweeping chain B while chain A is accepted.  Each chain's results are
+ * bit-identical to the same ctx run alone with pmp_run.  Requirements: one device, world_size 1, linear-Gaussian target, the
+ * same tree / algo in every ctx, and every ctx sharing ctxs[0]'s device copy of the data (pmp_share_data: dst aliases src's
+ * data without a copy; src must outlive dst's use of it).  This is the independent-repeats pattern of the reference's
+ * experiments (error.py:191-213 runs 20 repeats; the ESS runs use one process per GPU). */
+int pmp_share_data(pmp_ctx* dst, pmp_ctx* src);
+int pmp_run_multi(pmp_ctx** ctxs, int n_ctx, int64_t iters, int sync);
+int pmp_run_multi_timed(pmp_ctx** ctxs, int n_ctx, int64_t iters, float* total_ms);   /* CUDA events around the joint kernel; blocking */
 /* Copy out the rows recorded since the last pmp_trace_config / pmp_trace_reset (blocking); any pointer may be NULL. */
 int pmp_read_trace(pmp_ctx* ctx, int64_t max_iters, float* state, int32_t* next, int32_t* draws, float* samples,
                    double* logw, int64_t* n_recorded);

@@ -25,7 +25,7 @@ EXPORTS = [
     "pmp_accept", "pmp_read_logweights", "pmp_trace_config", "pmp_run", "pmp_sync", "pmp_read_trace", "pmp_trace_reset",
     "pmp_run_timed", "pmp_launch_count", "pmp_fp32_peak", "pmp_l2_flush", "pmp_chains_create", "pmp_chains_run",
     "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
-    "pmp_stream_normals", "pmp_time_sweep",
+    "pmp_stream_normals", "pmp_time_sweep", "pmp_share_data", "pmp_run_multi", "pmp_run_multi_timed",
 ]
 
 
@@ -106,10 +106,29 @@ def load():
     L.pmp_set_data_fc.argtypes = [vp, vp, vp, i64, i64, i64]
     L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
+    L.pmp_share_data.argtypes = [vp, vp]
+    L.pmp_run_multi.argtypes = [ctypes.POINTER(vp), i32, i64, i32]
+    L.pmp_run_multi_timed.argtypes = [ctypes.POINTER(vp), i32, i64, ctypes.POINTER(ctypes.c_float)]
     if L.pmp_abi_version() != 1:
         raise PmpError("libpmp_b200.so ABI version mismatch")
     _lib = L
     return L
+
+
+def _handles(ctxs):
+    arr = (ctypes.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    return arr
+
+
+def run_multi(ctxs, iters, sync=True):
+    """Co-scheduled independent chains (pmp_run_multi): one cooperative kernel sweeps chain B while chain A is accepted."""
+    ctxs[0]._chk(ctxs[0].L.pmp_run_multi(_handles(ctxs), len(ctxs), iters, 1 if sync else 0))
+
+
+def run_multi_timed(ctxs, iters):
+    ms = ctypes.c_float()
+    ctxs[0]._chk(ctxs[0].L.pmp_run_multi_timed(_handles(ctxs), len(ctxs), iters, ctypes.byref(ms)))
+    return ms.value
 
 
 def stream_uniforms(seed, iteration, stream, idx0, count):
@@ -257,14 +276,29 @@ class Context:
     def sync(self):
         self._chk(self.L.pmp_sync(self.h))
 
-    def read_trace(self, max_iters=None):
+    def share_data_from(self, owner):
+        """Alias `owner`'s device copy of the linear-Gaussian data (no copy); `owner` must stay alive while this ctx uses it."""
+        self._chk(self.L.pmp_share_data(self.h, owner.h))
+        self._data_owner = owner
+
+    def trace_buffers(self, max_iters=None, pinned=False):
+        """Host arrays shaped for read_trace(out=...); pinned=True allocates them page-locked through torch."""
         n = self._trace_cap if max_iters is None else min(max_iters, self._trace_cap)
         w, P, d = self._trace_what, self.P, self.cfg.dim
-        state = np.empty((n, d), np.float32) if w & TRACE_STATE else None
-        nxt = np.empty(n, np.int32) if w & TRACE_NEXT else None
-        draws = np.empty((n, P), np.int32) if w & TRACE_DRAWS else None
-        samples = np.empty((n, P, d), np.float32) if w & TRACE_SAMPLES else None
-        logw = np.empty((n, P), np.float64) if w & TRACE_LOGW else None
+
+        def mk(shape, dt):
+            if pinned:
+                import torch
+                return torch.empty(shape, dtype={np.float32: torch.float32, np.int32: torch.int32, np.float64: torch.float64}[dt]).pin_memory().numpy()
+            return np.empty(shape, dt)
+        return {"state": mk((n, d), np.float32) if w & TRACE_STATE else None, "next": mk((n,), np.int32) if w & TRACE_NEXT else None,
+                "draws": mk((n, P), np.int32) if w & TRACE_DRAWS else None, "samples": mk((n, P, d), np.float32) if w & TRACE_SAMPLES else None,
+                "logw": mk((n, P), np.float64) if w & TRACE_LOGW else None}
+
+    def read_trace(self, max_iters=None, out=None):
+        n = self._trace_cap if max_iters is None else min(max_iters, self._trace_cap)
+        b = out if out is not None else self.trace_buffers(max_iters)
+        state, nxt, draws, samples, logw = b["state"], b["next"], b["draws"], b["samples"], b["logw"]
         rec = ctypes.c_int64()
         self._chk(self.L.pmp_read_trace(self.h, n, _ptr(state), _ptr(nxt), _ptr(draws), _ptr(samples), _ptr(logw), ctypes.byref(rec)))
         r = rec.value

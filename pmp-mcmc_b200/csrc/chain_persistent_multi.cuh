@@ -1,0 +1,183 @@
+// chain_persistent_multi.cuh — K independent chains co-scheduled in ONE cooperative kernel (single GPU, linear-Gaussian target).
+//
+// Why.  A single chain is a strict dependency loop: sweep (all SMs) → acceptance (one SM, ~3 us critical path + two L2
+// hand-offs) → next sweep.  In chain_persistent_kernel the 147 sweep SMs idle for ~8 of every ~19.7 us while the acceptance of
+// THEIR OWN chain runs; nothing of that chain can be started earlier.  The reference's experiments are run as several
+// independent chains (20 repeats in error.py:191-213, one process per GPU in the ESS runs, 4 chains for any R-hat); with K >= 2
+// chains resident the sweep SMs simply work on chain B while chain A is being accepted:
+//     sweep SMs, warps  0-15 :  | sweep A_i  ....... | wait, nodes | sweep A_i+1 ....... |
+//     sweep SMs, warps 16-31 :  ..... | flush | wait, nodes | sweep B_i ....... | flush |
+//     acceptance CTAs (2)    :  one per chain parity: pre during the sweep, crit when the sums are in, post after the release
+// Every chain keeps its own pmp_ctx (state, Philox key, nodes, integer sums, counters, trace ring), executes exactly the
+// arithmetic of chain_persistent_kernel in exactly the same order, and therefore produces bit-identical traces to the same
+// chain run alone (tests/test_gpu_multichain.py).  The data slice of a sweep CTA is staged into shared memory once and is
+// shared by all chains (pmp_share_data makes the contexts alias one device copy of the data).
+#pragma once
+#include "chain_persistent.cuh"
+
+namespace pmp {
+
+constexpr int PERSIST_MAX_CHAINS = 4;
+
+struct PersistChain {
+    SweepArgs sw;
+    AcceptFastArgs fa;
+    PersistSync* sync;
+};
+
+struct PersistMultiArgs {
+    PersistChain ch[PERSIST_MAX_CHAINS];
+    int n_chains;
+    int iters;
+    int max_chunks;
+};
+
+__device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(PERSIST_THREADS / 2) : "memory"); }
+
+// Roles.  CTAs [0, n_sweep) sweep; the last n_accept = min(K, 2) CTAs accept (acceptance CTA a serves chains a, a+2, ...).
+// A sweep CTA is split into two independent halves of 512 threads (16 warps each, private named barrier): half h serves chains
+// h, h+2, ...  While one half waits for its chain's acceptance, reads its nodes or flushes its sums — all L2 round trips — the
+// other half's packed-FMA loop has the SM's FP32 pipe to itself, so the pipe only idles when BOTH halves are between sweeps.
+// The per-node sums are integers, so splitting the chunk lanes 16 + 16 instead of 32 changes no bit of the result.
+template <int ALGO>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_kernel(const __grid_constant__ PersistMultiArgs pa) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int tid = threadIdx.x;
+    const int K = pa.n_chains;
+    const int n_accept = K < 2 ? 1 : 2;
+    const int n_sweep = gridDim.x - n_accept;
+
+    if ((int)blockIdx.x >= n_sweep) {
+        // ================= acceptance CTAs: their chains in round-robin order, one three-phase acceptance each ============
+        __shared__ double red[4][32];
+        __shared__ int s_pick;
+        const LeanSmem ls = lean_carve(dsm, pa.ch[0].fa.base.P, ALGO);
+        LeanRegs lr;
+        for (int it = 0; it < pa.iters; ++it) {
+            for (int c = (int)blockIdx.x - n_sweep; c < K; c += n_accept) {
+                const AcceptFastArgs& fa = pa.ch[c].fa;
+                lean_pre<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
+                if (tid == 0) spin_until_ge(&pa.ch[c].sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
+                __syncthreads();
+                lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) st_release(&pa.ch[c].sync->version, (unsigned)(it + 1));
+                lean_post<ALGO>(fa, ls, lr);
+                __threadfence();          // trace cursor and state are read back by the next pre of this chain / by the host
+                __syncthreads();
+            }
+        }
+        return;
+    }
+
+    // ================= sweep CTAs =================
+    constexpr int R = PERSIST_R, TP = PERSIST_TP, PT = PERSIST_PT;
+    constexpr int HT = PERSIST_THREADS / 2, TDH = HT / TP;                                  // threads / chunk lanes of one half
+    const SweepArgs& a0 = pa.ch[0].sw;                                                      // data, shapes: the same for every chain
+    float* tile = reinterpret_cast<float*>(dsm);                                           // [max_chunks][CHUNK_STRIDE], read-only after staging
+    const int half = tid / HT, htid = tid - half * HT;
+    unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE) + (size_t)half * TDH * PT;   // [TDH][PT] per half
+    __shared__ float sprops_all[2][PT * 3];
+    __shared__ double sscl_all[2][PT];
+    float* sprops = sprops_all[half];
+    double* sscl = sscl_all[half];
+
+    const int tp = htid & (TP - 1), td = htid / TP;
+    const int P = a0.P;
+    const long long nchunks = a0.nchunks, n_local = a0.n_local;
+    const int ntiles = (P + PT - 1) / PT;
+    const long long units = (long long)ntiles * nchunks;
+    const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
+
+    // ---- stage this CTA's data slice once (all 1024 threads): segment s covers chunks [c_begin, c_end) of node tile ptile --
+    int nseg = 0; int seg_tile[3]; long long seg_c0[3], seg_c1[3]; int seg_slot[3];
+    {
+        long long u = u_begin; int slot = 0;
+        while (u < u_end && nseg < 3) {
+            int ptile = (int)(u / nchunks);
+            long long c0 = u - (long long)ptile * nchunks, c1 = min(nchunks, c0 + (u_end - u));
+            seg_tile[nseg] = ptile; seg_c0[nseg] = c0; seg_c1[nseg] = c1; seg_slot[nseg] = slot;
+            for (long long i = tid; i < (c1 - c0) * (CHUNK / 2); i += PERSIST_THREADS) {
+                int c = (int)(i / (CHUNK / 2)), k = (int)(i - (long long)c * (CHUNK / 2));
+                bool isy = k >= CHUNK / 4; int kk = isy ? k - CHUNK / 4 : k;
+                long long g = (c0 + c) * CHUNK + 4 * kk;
+                const float* src = (isy ? a0.y : a0.x) + (g < n_local ? g : 0);
+                cp_async16(tile + (size_t)(slot + c) * CHUNK_STRIDE + (isy ? CHUNK : 0) + 4 * kk, src, g < n_local ? 16 : 0);
+            }
+            slot += (int)(c1 - c0); u += c1 - c0; ++nseg;
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    // this half's chains: half, half + 2 (K <= 4): Philox iteration of the chain at launch, read before any acceptance can advance it
+    unsigned long long iter0[2];
+    iter0[0] = (half < K) ? __ldcg(&pa.ch[half].sw.cnt->iteration) : 0ull;
+    iter0[1] = (half + 2 < K) ? __ldcg(&pa.ch[half + 2].sw.cnt->iteration) : 0ull;
+    bool sat0 = false, sat1 = false;
+
+    for (int it = 0; it < pa.iters; ++it) {
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+            const int c = half + 2 * q;
+            if (c >= K) break;
+            const SweepArgs& a = pa.ch[c].sw;
+            if (htid == 0 && it > 0) spin_until_ge(&pa.ch[c].sync->version, (unsigned)it);
+            half_sync(half);
+            {   // side job: this CTA's slice of the chain's NEXT-iteration normals (they depend on counters only)
+                const int zcount = P * 3, per = (zcount + n_sweep - 1) / n_sweep;
+                const unsigned long long iter = (q ? iter0[1] : iter0[0]) + (unsigned long long)it;
+                for (int k = HT - 1 - htid; k < per; k += HT) {
+                    const int e = blockIdx.x * per + k;
+                    if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+                }
+            }
+            bool sat = false;
+            for (int s = 0; s < nseg; ++s) {
+                const int node_base = seg_tile[s] * PT;
+                for (int i = htid; i < PT * 3; i += HT) {
+                    int node = node_base + i / 3, j = i - (i / 3) * 3;
+                    float v = (node < P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
+                    sprops[i] = v;
+                    if (j == 2) sscl[i / 3] = (node < P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+                }
+                half_sync(half);
+                float b0[R], b1[R]; double scl[R]; unsigned long long accq[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { int i = tp * R + r; b0[r] = sprops[3 * i]; b1[r] = sprops[3 * i + 1]; scl[r] = sscl[i]; accq[r] = 0ull; }
+                const int nct = (int)(seg_c1[s] - seg_c0[s]);
+                for (int cc = td; cc < nct; cc += TDH) {
+                    int cnt = (int)min((long long)CHUNK, n_local - (seg_c0[s] + cc) * CHUNK);
+                    float part[R];
+                    const float* sx = tile + (size_t)(seg_slot[s] + cc) * CHUNK_STRIDE;
+                    chunk_sumsq<R, true>(sx, sx + CHUNK, cnt, b0, b1, part);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        double dq = (double)part[r] * scl[r];
+                        if (!(dq < a.sat_limit)) { dq = a.sat_limit; sat = true; }
+                        accq[r] += (unsigned long long)__double2ll_rn(dq);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) sred[td * PT + tp * R + r] = accq[r];
+                half_sync(half);
+                for (int i = htid; i < PT; i += HT) {
+                    unsigned long long sum = 0ull;
+                    for (int k = 0; k < TDH; ++k) sum += sred[k * PT + i];
+                    if (node_base + i < P && sum) atomicAdd(a.acc + node_base + i, sum);
+                }
+                half_sync(half);
+            }
+            if (q) sat1 |= sat; else sat0 |= sat;
+            __threadfence();
+            half_sync(half);
+            if (htid == 0) atomicAdd(&pa.ch[c].sync->arrive, 1u);
+        }
+    }
+    if (sat0 && half < K) atomicOr(&pa.ch[half].sw.cnt->flags, 1);
+    if (sat1 && half + 2 < K) atomicOr(&pa.ch[half + 2].sw.cnt->flags, 1);
+}
+
+}  // namespace pmp

@@ -72,6 +72,8 @@ struct pmp_ctx {
     float* d_x = nullptr; float* d_y = nullptr;
     uint8_t* d_bimg = nullptr;         // [nchunks][2048] bf16 data operand image of the tensor-core sweep (sweep_linear_tc.cuh)
     long long n_local = 0, n_offset = 0, n_global = 0;
+    size_t data_capacity = 0;          // padded float count d_x / d_y were allocated for
+    bool data_borrowed = false;        // d_x / d_y / d_bimg alias another ctx's buffers (pmp_share_data): never freed here
 
     // chain
     uint64_t seed = 0;
@@ -116,4 +118,7 @@ struct pmp_ctx {
 
     // FC model
     void* fc = nullptr;
+
+    // MP kernel term for long parameter vectors (pmp_large_dim_kernel_term)
+    float* d_kt_s1 = nullptr; double* d_kt_dj2 = nullptr; double* d_kt_dot = nullptr; long long kt_dim_cap = 0;
 };

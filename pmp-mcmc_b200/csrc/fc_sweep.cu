@@ -263,6 +263,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 }
 
 enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1 };
+constexpr int GEMM2_EPI_WARPS = 8;                               // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int GEMM2_THREADS = 64 + 32 * GEMM2_EPI_WARPS;
 
 struct Gemm2Args {
     int M;                    // data rows of this shard
@@ -280,7 +282,7 @@ struct Gemm2Args {
 };
 
 template <int BN, int EPI, int NSTAGE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int BH = BN / 2;                                   // weight rows each CTA of the pair loads
@@ -293,6 +295,7 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_w4[EPI == EPI2_L4_NLL ? H3 * 12 : 4];
     __shared__ float s_b3[EPI == EPI2_L4_NLL ? H3 : 1], s_b4[EPI == EPI2_L4_NLL ? NCLS_PAD : 1];
+    __shared__ float s_z[EPI == EPI2_L4_NLL ? BM * (NCLS + 1) : 1];     // partial logits of the upper column half, [row][11]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -304,7 +307,7 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }   // 4 epilogue warps x 2 CTAs
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * GEMM2_EPI_WARPS); }   // epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                             // the same warp of BOTH CTAs allocates (and later frees) jointly
@@ -362,32 +365,35 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 umma_commit_2sm(&tfull_bar[acc]);                // accumulator stage complete, seen by both CTAs' epilogue warps
             }
         }
-    } else {                                                     // ===== epilogue warps 2..5 (both CTAs) =====
+    } else {                                                     // ===== epilogue warps 2..9 (both CTAs) =====
         const int quarter = warp & 3;                            // TMEM lanes [32q, 32q+32) are the only ones this warp may read
-        const int et = (warp - 2) * 32 + lane;                   // 0..127
+        const int chalf = (warp - 2) >> 2;                       // which half of the tile's columns this warp converts
+        const int et = (warp - 2) * 32 + lane;                   // 0..255
+        constexpr int CH = BN / 2;                               // columns per warp
         const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
         int j = 0;
         for (int t = pair; t < total; t += npairs, ++j) {
             const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
             const int acc = j & 1, use = j >> 1;
-            const int row = m_blk * 2 * BM + (int)rank * BM + quarter * 32 + lane;
+            const int lrow = quarter * 32 + lane;                // row inside this CTA's 128
+            const int row = m_blk * 2 * BM + (int)rank * BM + lrow;
             if (EPI == EPI2_L4_NLL) {                            // this node's last layer -> shared memory (transposed, 12-float rows)
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // everybody is done with the previous tile's copy
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // everybody is done with the previous tile's copy
                 const float* th = g.theta + (long long)batch * g.theta_stride;
-                for (int i = et; i < NCLS * H3; i += 128) { const int c = i / H3, jj = i - c * H3; s_w4[jj * 12 + c] = __ldg(th + OFF_W4 + i); }
-                s_b3[et] = __ldg(g.bias + (long long)batch * g.bias_stride + et);
+                for (int i = et; i < NCLS * H3; i += 32 * GEMM2_EPI_WARPS) { const int c = i / H3, jj = i - c * H3; s_w4[jj * 12 + c] = __ldg(th + OFF_W4 + i); }
+                if (et < H3) s_b3[et] = __ldg(g.bias + (long long)batch * g.bias_stride + et);
                 if (et < NCLS) s_b4[et] = __ldg(th + OFF_B4 + et);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(&tfull_bar[acc], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * CH);
             if (EPI == EPI2_RELU_SPLIT) {
-                const float* bias = g.bias + (long long)batch * g.bias_stride + n_blk * BN;
+                const float* bias = g.bias + (long long)batch * g.bias_stride + n_blk * BN + chalf * CH;
                 const long long ldo = 2ll * g.n_total;
-                __nv_bfloat16* orow = g.out + ((long long)batch * g.M + row) * ldo + n_blk * BN;
+                __nv_bfloat16* orow = g.out + ((long long)batch * g.M + row) * ldo + n_blk * BN + chalf * CH;
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 32; ++cc) {
+                for (int cc = 0; cc < CH / 32; ++cc) {
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
                     uint32_t hp[16], lp[16];
@@ -409,17 +415,20 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);   // this accumulator stage may be overwritten
             } else {
                 float z[NCLS];
 #pragma unroll
-                for (int c = 0; c < NCLS; ++c) z[c] = s_b4[c];
+                for (int c = 0; c < NCLS; ++c) z[c] = chalf == 0 ? s_b4[c] : 0.f;
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 32; ++cc) {
+                for (int cc = 0; cc < CH / 32; ++cc) {
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int jj = cc * 32 + i;
+                        const int jj = chalf * CH + cc * 32 + i;
                         const float a = fmaxf(__uint_as_float(v[i]) + s_b3[jj], 0.f);
                         const float4 w0 = *reinterpret_cast<const float4*>(&s_w4[jj * 12]);
                         const float4 w1 = *reinterpret_cast<const float4*>(&s_w4[jj * 12 + 4]);
@@ -429,28 +438,38 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         z[8] = fmaf(a, w2.x, z[8]); z[9] = fmaf(a, w2.y, z[9]);
                     }
                 }
-                float mx = z[0];
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);   // TMEM has been read: the stage may be overwritten
+                // the warp of the upper column half hands its partial logits to the warp of the lower half (same rows)
+                if (chalf == 1) {
 #pragma unroll
-                for (int c = 1; c < NCLS; ++c) mx = fmaxf(mx, z[c]);
-                float se = 0.f;
-#pragma unroll
-                for (int c = 0; c < NCLS; ++c) se += expf(z[c] - mx);
-                float nll = 0.f;
-                if (row < g.M) {
-                    const int lab = g.labels[row];
-                    float zl = z[0];
-#pragma unroll
-                    for (int c = 1; c < NCLS; ++c) zl = (lab == c) ? z[c] : zl;
-                    nll = (mx + logf(se)) - zl;
+                    for (int c = 0; c < NCLS; ++c) s_z[lrow * (NCLS + 1) + c] = z[c];
                 }
-                // per-row NLL -> 2^-32 fixed point; everything after this line is integer (exact, order-free)
-                long long q = (row < g.M) ? __double2ll_rn((double)nll * 4294967296.0) : 0ll;
-                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-                if (lane == 0 && q != 0) atomicAdd(g.loss + batch, (unsigned long long)q);
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (chalf == 0) {
+#pragma unroll
+                    for (int c = 0; c < NCLS; ++c) z[c] += s_z[lrow * (NCLS + 1) + c];
+                    float mx = z[0];
+#pragma unroll
+                    for (int c = 1; c < NCLS; ++c) mx = fmaxf(mx, z[c]);
+                    float se = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCLS; ++c) se += expf(z[c] - mx);
+                    float nll = 0.f;
+                    if (row < g.M) {
+                        const int lab = g.labels[row];
+                        float zl = z[0];
+#pragma unroll
+                        for (int c = 1; c < NCLS; ++c) zl = (lab == c) ? z[c] : zl;
+                        nll = (mx + logf(se)) - zl;
+                    }
+                    // per-row NLL -> 2^-32 fixed point; everything after this line is integer (exact, order-free)
+                    long long q = (row < g.M) ? __double2ll_rn((double)nll * 4294967296.0) : 0ll;
+                    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                    if (lane == 0 && q != 0) atomicAdd(g.loss + batch, (unsigned long long)q);
+                }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);   // this accumulator stage may be overwritten
         }
     }
     __syncwarp();
@@ -537,13 +556,16 @@ __global__ void fc_dots_kernel(const float* __restrict__ theta, const float* __r
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
     if ((threadIdx.x & 31) == 0) { atomicAdd(dj2 + p, a); atomicAdd(dot + p, b); }
 }
-__global__ void fc_kterm_kernel(const double* dj2, const double* dot, int P, double dim, double ks, double* logw) {
+// mean_kernel: MP_FC.py:107-114 (sum_k mean_dim logK / P); otherwise the plain sum over k and coordinates (lb.py:144-150)
+__global__ void fc_kterm_kernel(const double* dj2, const double* dot, int P, double dim, double ks, double* logw, int mean_kernel) {
     __shared__ double sS2;
     if (threadIdx.x == 0) { double s = 0.0; for (int p = 0; p < P; ++p) s += dj2[p]; sS2 = s; }
     __syncthreads();
+    const double log_norm_k = -0.91893853320467274178 - log(ks);
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         double sumsq = (double)P * dj2[p] - 2.0 * dot[p] + sS2;
-        logw[p] = ((double)(P - 1) * (-0.91893853320467274178 - log(ks)) - 0.5 * sumsq / (ks * ks) / dim) / (double)P;
+        logw[p] = mean_kernel ? ((double)(P - 1) * log_norm_k - 0.5 * sumsq / (ks * ks) / dim) / (double)P
+                              : (double)(P - 1) * dim * log_norm_k - 0.5 * sumsq / (ks * ks);
     }
 }
 
@@ -596,7 +618,7 @@ static int launch_gemm2(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, 
     long long pairs = c->sm_count / 2;
     if (pairs > tiles) pairs = tiles;
     if (pairs < 1) pairs = 1;
-    fc_gemm2_kernel<BN, EPI, NSTAGE><<<dim3((unsigned)(2 * pairs)), GEMM_THREADS, smem, c->stream>>>(a, b, g);   // cluster dims (2,1,1) are a kernel attribute
+    fc_gemm2_kernel<BN, EPI, NSTAGE><<<dim3((unsigned)(2 * pairs)), GEMM2_THREADS, smem, c->stream>>>(a, b, g);   // cluster dims (2,1,1) are a kernel attribute
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
@@ -627,6 +649,7 @@ using namespace pmp::fc;
 extern "C" {
 
 int pmp_allreduce_u64(pmp_ctx* c, unsigned long long* buf, size_t count);   // pmp_abi.cu
+int pmp_large_dim_kernel_term(pmp_ctx* c);
 
 int pmp_fc_destroy(pmp_ctx* c) {
     if (c->fc) { free_state(reinterpret_cast<FcState*>(c->fc)); delete reinterpret_cast<FcState*>(c->fc); c->fc = nullptr; }
@@ -744,15 +767,28 @@ int pmp_fc_loglik(pmp_ctx* c) {
     if ((rc = pmp_allreduce_u64(c, s->loss, (size_t)P))) return rc;
     finalize_loss_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(s->loss, c->d_lt, P, (double)s->n_global, 1.0 / (double)c->cfg.scale);
     c->launches++;
-    if (c->cfg.algo == PMP_ALGO_MP && !(c->cfg.flags & PMP_FLAG_NO_KERNEL_TERM)) {
-        if (!s->s1) { PMP_CUDA(cudaMalloc((void**)&s->s1, (size_t)THETA_DIM * sizeof(float))); PMP_CUDA(cudaMalloc((void**)&s->dj2, MAX_NODES * sizeof(double))); PMP_CUDA(cudaMalloc((void**)&s->dot, MAX_NODES * sizeof(double))); }
-        PMP_CUDA(cudaMemsetAsync(s->dj2, 0, P * sizeof(double), c->stream));
-        PMP_CUDA(cudaMemsetAsync(s->dot, 0, P * sizeof(double), c->stream));
-        fc_s1_kernel<<<(unsigned)((THETA_DIM + 255) / 256), 256, 0, c->stream>>>(c->d_props, THETA_DIM, P, s->s1);
-        fc_dots_kernel<<<dim3(64, P), 256, 0, c->stream>>>(c->d_props, s->s1, THETA_DIM, s->dj2, s->dot);
-        fc_kterm_kernel<<<1, 256, 0, c->stream>>>(s->dj2, s->dot, P, (double)THETA_DIM, (double)c->cfg.kernel_sigma, c->d_logw);
-        c->launches += 3;
+    if (c->cfg.algo == PMP_ALGO_MP && !(c->cfg.flags & PMP_FLAG_NO_KERNEL_TERM)) { if ((rc = pmp_large_dim_kernel_term(c))) return rc; }
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+// MP proposal-kernel term of every node for parameter vectors too long for the acceptance kernel's shared memory
+// (dim > KDIM_MAX: the FC model, arbitrary networks behind PMP_TARGET_EXTERNAL), closed form about node 0, into d_logw.
+int pmp_large_dim_kernel_term(pmp_ctx* c) {
+    const int P = c->P; const long long dim = c->cfg.dim;
+    if (c->kt_dim_cap < dim) {
+        if (c->d_kt_s1) cudaFree(c->d_kt_s1);
+        c->d_kt_s1 = nullptr; c->kt_dim_cap = 0;
+        PMP_CUDA(cudaMalloc((void**)&c->d_kt_s1, (size_t)dim * sizeof(float)));
+        c->kt_dim_cap = dim;
     }
+    if (!c->d_kt_dj2) { PMP_CUDA(cudaMalloc((void**)&c->d_kt_dj2, MAX_NODES * sizeof(double))); PMP_CUDA(cudaMalloc((void**)&c->d_kt_dot, MAX_NODES * sizeof(double))); }
+    PMP_CUDA(cudaMemsetAsync(c->d_kt_dj2, 0, P * sizeof(double), c->stream));
+    PMP_CUDA(cudaMemsetAsync(c->d_kt_dot, 0, P * sizeof(double), c->stream));
+    fc_s1_kernel<<<(unsigned)((dim + 255) / 256), 256, 0, c->stream>>>(c->d_props, dim, P, c->d_kt_s1);
+    fc_dots_kernel<<<dim3(64, P), 256, 0, c->stream>>>(c->d_props, c->d_kt_s1, dim, c->d_kt_dj2, c->d_kt_dot);
+    fc_kterm_kernel<<<1, 256, 0, c->stream>>>(c->d_kt_dj2, c->d_kt_dot, P, (double)dim, (double)c->cfg.kernel_sigma, c->d_logw, (c->cfg.flags & PMP_FLAG_KERNEL_MEAN) ? 1 : 0);
+    c->launches += 3;
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
 }

@@ -11,6 +11,7 @@
 #include "accept_lean.cuh"
 #include "chain_persistent.cuh"
 #include "chain_persistent_tc.cuh"
+#include "chain_persistent_multi.cuh"
 #include "common.cuh"
 #include "sweep_linear.cuh"
 #include "sweep_linear_tc.cuh"
@@ -330,8 +331,9 @@ int pmp_destroy(pmp_ctx* c) {
     pmp_fc_destroy(c);
     pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
+    if (c->data_borrowed) { c->d_x = nullptr; c->d_y = nullptr; c->d_bimg = nullptr; }     // owned by another ctx (pmp_share_data)
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
-                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_bimg};
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_bimg, c->d_kt_s1, c->d_kt_dj2, c->d_kt_dot};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -373,8 +375,8 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     if (cfg->algo == PMP_ALGO_MH || cfg->algo == PMP_ALGO_BARKER) PMP_REQUIRE(P == 2, "MH/BARKER need P == 2 (FLAT, b=2), got %lld", P);
     if (cfg->algo == PMP_ALGO_PSP) PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY, "PSP needs the BINARY tree");
     if (cfg->algo == PMP_ALGO_PMP) PMP_REQUIRE(cfg->tree == PMP_TREE_BARY || cfg->tree == PMP_TREE_BINARY, "PMP needs a BARY/BINARY tree");
-    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC)
-        PMP_REQUIRE(cfg->dim <= KDIM_MAX, "in-kernel MP kernel term supports dim <= %d", KDIM_MAX);
+    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC && cfg->target != PMP_TARGET_EXTERNAL)
+        PMP_REQUIRE(cfg->dim <= KDIM_MAX, "in-kernel MP kernel term supports dim <= %d for this target", KDIM_MAX);
     PMP_REQUIRE(cfg->scale != 0.f && cfg->kernel_sigma > 0.f, "scale must be non-zero and kernel_sigma > 0");
 
     PMP_CUDA(cudaStreamSynchronize(c->stream));
@@ -401,6 +403,7 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     c->lt_valid = false; c->acc_pending = false;
     c->configured = true;
     // trace buffers depend on P and dim
+    { void* tb[] = {c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw}; for (void* p : tb) if (p) cudaFree(p); }
     c->trace = TraceBuffers{};
     return PMP_OK;
 }
@@ -418,10 +421,17 @@ int pmp_set_data_linear(pmp_ctx* c, const float* x, const float* y, int64_t n_lo
     PMP_CUDA(cudaSetDevice(c->device));
     PMP_CUDA(cudaStreamSynchronize(c->stream));
     drop_graph(c);
+    if (c->data_borrowed) { c->d_x = nullptr; c->d_y = nullptr; c->d_bimg = nullptr; c->data_borrowed = false; c->data_capacity = 0; }
     int rc;
     size_t padded = ((size_t)n_local + 3) / 4 * 4 + 4;
-    if ((rc = dev_alloc(&c->d_x, padded))) return rc;
-    if ((rc = dev_alloc(&c->d_y, padded))) return rc;
+    const long long nchunks = ((long long)n_local + CHUNK - 1) / CHUNK;
+    const bool reuse = c->d_x && c->d_y && c->data_capacity == padded && (c->d_bimg || nchunks == 0);   // same shard size: refill in place (contexts aliasing it stay valid)
+    if (!reuse) {
+        if ((rc = dev_alloc(&c->d_x, padded))) return rc;
+        if ((rc = dev_alloc(&c->d_y, padded))) return rc;
+        if ((rc = dev_alloc(&c->d_bimg, (size_t)nchunks * tc::CHUNK_BYTES))) return rc;
+        c->data_capacity = padded;
+    }
     PMP_CUDA(cudaMemsetAsync(c->d_x, 0, padded * sizeof(float), c->stream));
     PMP_CUDA(cudaMemsetAsync(c->d_y, 0, padded * sizeof(float), c->stream));
     if (n_local) {
@@ -429,8 +439,6 @@ int pmp_set_data_linear(pmp_ctx* c, const float* x, const float* y, int64_t n_lo
         PMP_CUDA(cudaMemcpyAsync(c->d_y, y, n_local * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
     // data operand of the tensor-core sweep: the shared-memory image of every 64-point chunk, written once
-    const long long nchunks = ((long long)n_local + CHUNK - 1) / CHUNK;
-    if ((rc = dev_alloc(&c->d_bimg, (size_t)nchunks * tc::CHUNK_BYTES))) return rc;
     if (nchunks) {
         tc::build_data_image_kernel<<<(unsigned)((nchunks * CHUNK + 255) / 256), 256, 0, c->stream>>>(c->d_x, c->d_y, n_local, nchunks, c->d_bimg);
         c->launches++;
@@ -503,6 +511,7 @@ int pmp_write_proposals(pmp_ctx* c, const float* in, int64_t count) {
 }
 
 int pmp_fc_loglik(pmp_ctx* c);   // fc_sweep.cu: fills d_lt for PMP_TARGET_FC
+int pmp_large_dim_kernel_term(pmp_ctx* c);   // fc_sweep.cu: MP kernel term for dim > KDIM_MAX into d_logw
 
 // internal (not in the public header): exact cross-rank sum of fixed-point partials on the ctx stream
 int pmp_allreduce_u64(pmp_ctx* c, unsigned long long* buf, size_t count) {
@@ -558,7 +567,10 @@ int pmp_accept(pmp_ctx* c, const double* uniforms, int64_t n_uniforms, int32_t* 
         PMP_CUDA(cudaMemcpyAsync(c->d_uniforms, uniforms, n_uniforms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         d_u = c->d_uniforms;
     }
-    int rc = launch_accept(c, 0, 0, 1, d_u);
+    int rc;
+    if (c->cfg.target == PMP_TARGET_EXTERNAL && c->cfg.algo == PMP_ALGO_MP && !(c->cfg.flags & PMP_FLAG_NO_KERNEL_TERM) && c->cfg.dim > KDIM_MAX)
+        if ((rc = pmp_large_dim_kernel_term(c))) return rc;         // kernel term of the current nodes, read by the acceptance from d_logw
+    rc = launch_accept(c, 0, 0, 1, d_u);
     if (rc) return rc;
     c->lt_valid = false;
     c->host_iter++;
@@ -584,6 +596,12 @@ int pmp_trace_config(pmp_ctx* c, int64_t max_iters, uint32_t what) {
     PMP_REQUIRE(max_iters >= 0, "max_iters < 0");
     PMP_CUDA(cudaSetDevice(c->device));
     PMP_CUDA(cudaStreamSynchronize(c->stream));
+    if (max_iters == c->trace.capacity && what == c->trace.what) {      // same ring: keep the buffers, rewind the cursor
+        long long zero0 = 0;
+        PMP_CUDA(cudaMemcpyAsync(&c->d_cnt->trace_rows, &zero0, sizeof(zero0), cudaMemcpyHostToDevice, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+        return PMP_OK;
+    }
     drop_graph(c);
     int rc;
     size_t n = (size_t)max_iters, P = c->P, dim = c->cfg.dim;
@@ -772,6 +790,141 @@ int pmp_run(pmp_ctx* c, int64_t iters, int sync) {
     if (rc) return rc;
     if (sync) PMP_CUDA(cudaStreamSynchronize(c->stream));
     return PMP_OK;
+}
+
+// ---- co-scheduled chains (chain_persistent_multi.cuh) ---------------------------------------------------------------------
+int pmp_share_data(pmp_ctx* dst, pmp_ctx* src) {
+    PMP_REQUIRE(dst && src && dst != src, "bad arguments");
+    PMP_REQUIRE(dst->device == src->device, "contexts live on different devices (%d, %d)", dst->device, src->device);
+    PMP_REQUIRE(src->d_x && !src->data_borrowed, "src owns no linear-Gaussian data (pmp_set_data_linear it first)");
+    PMP_CUDA(cudaSetDevice(dst->device));
+    PMP_CUDA(cudaStreamSynchronize(dst->stream));
+    PMP_CUDA(cudaStreamSynchronize(src->stream));
+    drop_graph(dst);
+    if (!dst->data_borrowed) { if (dst->d_x) cudaFree(dst->d_x); if (dst->d_y) cudaFree(dst->d_y); if (dst->d_bimg) cudaFree(dst->d_bimg); }
+    dst->d_x = src->d_x; dst->d_y = src->d_y; dst->d_bimg = src->d_bimg;
+    dst->n_local = src->n_local; dst->n_offset = src->n_offset; dst->n_global = src->n_global;
+    dst->data_borrowed = true;
+    dst->data_capacity = 0;
+    return PMP_OK;
+}
+
+static int run_impl(pmp_ctx* c, int64_t iters);
+
+// Sharded chains (world_size > 1): no joint kernel — every chain runs its own stepwise loop (sweep → NCCL all-reduce →
+// acceptance, CUDA-graph replayed) on its own stream with its own communicator, so one chain's all-reduce and one-CTA
+// acceptance overlap the other chains' sweeps.  Fork/join with events so that [ev_begin, ev_end] on ctx 0's stream
+// brackets all of it.
+static int run_multi_streams(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+    pmp_ctx* c0 = cs[0];
+    PMP_CUDA(cudaSetDevice(c0->device));
+    if (ev_begin) PMP_CUDA(cudaEventRecord(ev_begin, c0->stream));
+    PMP_CUDA(cudaEventRecord(c0->ev0, c0->stream));
+    for (int k = 1; k < K; ++k) PMP_CUDA(cudaStreamWaitEvent(cs[k]->stream, c0->ev0, 0));
+    int rc;
+    for (int k = 0; k < K; ++k) if ((rc = run_impl(cs[k], iters))) return rc;
+    for (int k = 1; k < K; ++k) {
+        PMP_CUDA(cudaEventRecord(cs[k]->ev1, cs[k]->stream));
+        PMP_CUDA(cudaStreamWaitEvent(c0->stream, cs[k]->ev1, 0));
+    }
+    if (ev_end) PMP_CUDA(cudaEventRecord(ev_end, c0->stream));
+    return PMP_OK;
+}
+
+static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+    PMP_REQUIRE(cs && K >= 1 && K <= PERSIST_MAX_CHAINS, "1..%d contexts", PERSIST_MAX_CHAINS);
+    PMP_REQUIRE(iters >= 2 && iters <= 2000000000ll, "iters out of range");
+    pmp_ctx* c0 = cs[0];
+    PMP_REQUIRE(c0 && c0->configured, "ctx 0 not configured");
+    if (c0->world > 1) {
+        for (int k = 0; k < K; ++k) {
+            PMP_REQUIRE(cs[k] && cs[k]->configured && cs[k]->device == c0->device && cs[k]->world == c0->world && cs[k]->rank == c0->rank, "ctx %d: not configured or another rank / device", k);
+            for (int j = 0; j < k; ++j) PMP_REQUIRE(cs[j] != cs[k], "ctx %d given twice", k);
+        }
+        return run_multi_streams(cs, K, iters, ev_begin, ev_end);
+    }
+    for (int k = 0; k < K; ++k) {
+        pmp_ctx* c = cs[k];
+        PMP_REQUIRE(c && c->configured, "ctx %d not configured", k);
+        for (int j = 0; j < k; ++j) PMP_REQUIRE(cs[j] != c, "ctx %d given twice", k);
+        PMP_REQUIRE(c->device == c0->device && c->world == 1, "co-scheduled chains: one device, world_size 1");
+        PMP_REQUIRE(c->cfg.target == PMP_TARGET_LINEAR_GAUSS && lean_accept_ok(c) && !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL),
+                    "co-scheduled chains need the linear-Gaussian target with a device-resident acceptance rule (MP / PSP / TABLE quirk), P <= %d", LEAN_MAX_P);
+        PMP_REQUIRE(c->P == c0->P && c->cfg.algo == c0->cfg.algo && c->cfg.dim == c0->cfg.dim, "ctx %d: P / algo differ from ctx 0", k);
+        PMP_REQUIRE(c->d_x == c0->d_x && c->d_y == c0->d_y && c->n_local == c0->n_local && c->n_global == c0->n_global,
+                    "ctx %d does not share ctx 0's data (pmp_share_data)", k);
+    }
+    PMP_CUDA(cudaSetDevice(c0->device));
+    const int G = c0->sm_count, n_sweep = G - (K < 2 ? 1 : 2);     // one acceptance CTA per chain parity
+    const long long nchunks = (c0->n_local + CHUNK - 1) / CHUNK;
+    PMP_REQUIRE(nchunks > 0 && n_sweep >= 1, "no data");
+    const int ntiles = (c0->P + PERSIST_PT - 1) / PERSIST_PT;
+    const long long units = (long long)ntiles * nchunks;
+    const long long max_chunks = (units + n_sweep - 1) / n_sweep + 1;
+    const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
+    const size_t accept_smem = lean_smem_bytes(c0->P, c0->cfg.algo);
+    const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
+    if (smem > 200 * 1024) { set_error("co-scheduled chains: a sweep CTA's data slice (%zu bytes) does not fit shared memory", smem); return PMP_ERR_UNSUPPORTED; }
+    PersistMultiArgs pa{};
+    int rc;
+    for (int k = 0; k < K; ++k) {
+        pmp_ctx* c = cs[k];
+        if (!c->d_psync) { PMP_CUDA(cudaMalloc((void**)&c->d_psync, sizeof(PersistSync))); }
+        PMP_CUDA(cudaMemsetAsync(c->d_psync, 0, sizeof(PersistSync), c->stream));
+        if ((rc = launch_propose(c))) return rc;                   // nodes of the first iteration; later ones come from the acceptance CTA
+        const ProposeArgs gen{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, 0};
+        pa.ch[k].sw = SweepArgs{c->d_x, c->d_y, c->d_props, c->d_acc, c->d_cnt, c->n_local, nchunks, c->P, PERSIST_TP, PERSIST_TD, sat_limit(c), 0, c->d_z, gen, nullptr};
+        AcceptArgs aa = make_accept_args(c, 1, 0, 1, nullptr);
+        aa.dbg = nullptr;
+        pa.ch[k].fa = AcceptFastArgs{aa, c->d_z, 1, gen};
+        pa.ch[k].sync = reinterpret_cast<PersistSync*>(c->d_psync);
+        PMP_CUDA(cudaStreamSynchronize(c->stream));                // everything queued on this chain's own stream is done before the joint launch
+    }
+    pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks;
+    void* kargs[] = {&pa};
+    const void* fn;
+    switch (c0->cfg.algo) {
+        case PMP_ALGO_MP: fn = (const void*)chain_persistent_multi_kernel<PMP_ALGO_MP>; break;
+        case PMP_ALGO_PSP: fn = (const void*)chain_persistent_multi_kernel<PMP_ALGO_PSP>; break;
+        default: fn = (const void*)chain_persistent_multi_kernel<PMP_ALGO_TABLE>; break;
+    }
+    PMP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, smem));
+    if (per_sm < 1) { set_error("co-scheduled chains: the cooperative kernel does not fit an SM"); return PMP_ERR_UNSUPPORTED; }
+    if (ev_begin) PMP_CUDA(cudaEventRecord(ev_begin, c0->stream));
+    PMP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PERSIST_THREADS), kargs, smem, c0->stream));
+    if (ev_end) PMP_CUDA(cudaEventRecord(ev_end, c0->stream));
+    c0->launches++;
+    PMP_CUDA(cudaEventRecord(c0->ev1, c0->stream));
+    for (int k = 0; k < K; ++k) {
+        pmp_ctx* c = cs[k];
+        if (k > 0) PMP_CUDA(cudaStreamWaitEvent(c->stream, c0->ev1, 0));   // later work on the chain's own stream is ordered after the joint kernel
+        c->host_iter += (unsigned long long)iters;
+        c->z_valid_iter = -1;
+        c->lt_valid = false;
+    }
+    return PMP_OK;
+}
+
+int pmp_run_multi(pmp_ctx** ctxs, int n_ctx, int64_t iters, int sync) {
+    int rc = run_multi_impl(ctxs, n_ctx, iters, nullptr, nullptr);
+    if (rc) return rc;
+    if (sync) for (int k = 0; k < n_ctx; ++k) PMP_CUDA(cudaStreamSynchronize(ctxs[k]->stream));
+    return PMP_OK;
+}
+
+int pmp_run_multi_timed(pmp_ctx** ctxs, int n_ctx, int64_t iters, float* total_ms) {
+    PMP_REQUIRE(ctxs && n_ctx >= 1 && ctxs[0] && total_ms, "bad arguments");
+    cudaEvent_t e0, e1;
+    PMP_CUDA(cudaEventCreate(&e0)); PMP_CUDA(cudaEventCreate(&e1));
+    int rc = run_multi_impl(ctxs, n_ctx, iters, e0, e1);
+    if (rc == PMP_OK) {
+        for (int k = 0; k < n_ctx; ++k) cudaStreamSynchronize(ctxs[k]->stream);
+        if (cudaEventElapsedTime(total_ms, e0, e1) != cudaSuccess) { set_error("cudaEventElapsedTime failed"); rc = PMP_ERR_CUDA; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
 }
 
 int pmp_sync(pmp_ctx* c) {

@@ -75,8 +75,24 @@ def main():
         assert torch.equal(t, ref)
         for k in ("state", "next", "draws", "logw"):
             res[name + "_" + k] = tr[k]
+    # two sharded chains on two streams / two communicators (pmp_run_multi, streams mode): chain 0 repeats the "mp" run above,
+    # chain 1 is an independent chain with its own key — each must equal its solo run
+    ctx2 = pdist.create_context(local)
+    for c, seed in ((ctx, 99), (ctx2, 123)):
+        c.configure(0, b=256, depth=1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.02, scale=1000.0)
+    pdist.set_data_linear_sharded(ctx, x, y)
+    ctx2.share_data_from(ctx)
+    for c, seed in ((ctx, 99), (ctx2, 123)):
+        c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
+        c.trace_config(a.iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW)
+    L.run_multi([ctx, ctx2], a.iters)
+    for tag, c in (("co0", ctx), ("co1", ctx2)):
+        tr = c.read_trace()
+        for k in ("state", "next", "draws", "logw"):
+            res[tag + "_" + k] = tr[k]
     if rank == 0:
         np.savez(a.out, world=world, **res)
+    ctx2.close()
     ctx.close()
     td.destroy_process_group()
 

@@ -1,0 +1,79 @@
+"""Co-scheduled independent chains (pmp_run_multi, chain_persistent_multi.cuh): every chain's trace must be bit-identical to
+the same chain run alone with pmp_run — the kernel changes WHEN a chain's sweep runs, never what it computes."""
+import numpy as np
+import pytest
+
+from conftest import synthetic_linear
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # tree, b, depth, algo, draw, flags, P-ish label
+    ("mp_flat_1024", dict(tree="FLAT", b=1024, depth=1, algo="MP", draw="CUDA", flags=0, alpha=0.01, scale=100.0)),
+    ("psp_binary_d8", dict(tree="BINARY", b=2, depth=8, algo="PSP", draw="PYTHON", flags=0, alpha=0.02, scale=100.0)),
+    ("mp_flat_37", dict(tree="FLAT", b=37, depth=1, algo="MP", draw="PYTHON", flags=0, alpha=0.05, scale=10.0)),
+]
+
+
+def _configure(c, L, k):
+    c.configure(getattr(L, "TREE_" + k["tree"]), b=k["b"], depth=k["depth"], dim=3, target=L.TARGET_LINEAR_GAUSS, algo=getattr(L, "ALGO_" + k["algo"]),
+                draw=getattr(L, "DRAW_" + k["draw"]), flags=k["flags"], alpha=k["alpha"], scale=k["scale"])
+
+
+@pytest.mark.parametrize("name,k", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 4])
+def test_co_scheduled_chains_equal_solo_chains(name, k, n_chains):
+    import pmp_mcmc_b200 as pm
+    from pmp_mcmc_b200 import _lib as L
+    n, iters = 5000, 40
+    x, y = synthetic_linear(n, seed=3)
+    what = L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW
+    starts = [np.array([0.0, 0.0, 1.0], np.float32), np.array([-1.0, 2.0, 0.5], np.float32), np.array([0.5, 0.5, 2.0], np.float32), np.array([1.0, 1.0, 1.0], np.float32)]
+    solo = []
+    for i in range(n_chains):
+        c = pm.Context(0)
+        _configure(c, L, k)
+        c.set_data_linear(x, y); c.set_state(starts[i]); c.seed(100 + i, 0)
+        c.trace_config(iters, what)
+        c.run(iters)
+        solo.append((c.read_trace(), c.get_state(), c.iteration()))
+        c.close()
+    ctxs = []
+    for i in range(n_chains):
+        c = pm.Context(0)
+        _configure(c, L, k)
+        if i == 0:
+            c.set_data_linear(x, y)
+        else:
+            c.share_data_from(ctxs[0])
+        c.set_state(starts[i]); c.seed(100 + i, 0)
+        c.trace_config(iters, what)
+        ctxs.append(c)
+    L.run_multi(ctxs, iters)
+    for i, c in enumerate(ctxs):
+        tr, (ref, st, it) = c.read_trace(), solo[i]
+        assert tr["n"] == ref["n"] == iters
+        for key in ("state", "next", "draws"):
+            assert np.array_equal(tr[key], ref[key]), (name, i, key)
+        assert np.array_equal(tr["logw"].view(np.uint64), ref["logw"].view(np.uint64)), (name, i, "logw")
+        assert np.array_equal(c.get_state(), st) and c.iteration() == it
+    # the chains are independent: different seeds give different trajectories
+    if n_chains > 1:
+        assert not np.array_equal(ctxs[0].read_trace()["next"], ctxs[1].read_trace()["next"])
+    # a second joint run continues every chain where it stopped (counters and state live on the device)
+    L.run_multi(ctxs, 10)
+    assert all(c.iteration() == iters + 10 for c in ctxs)
+    for c in reversed(ctxs):
+        c.close()
+
+
+def test_run_multi_rejects_unshared_data():
+    import pmp_mcmc_b200 as pm
+    from pmp_mcmc_b200 import _lib as L
+    x, y = synthetic_linear(1000, seed=1)
+    a, b = pm.Context(0), pm.Context(0)
+    for c in (a, b):
+        _configure(c, L, CASES[0][1]); c.set_data_linear(x, y); c.set_state([0, 0, 1]); c.seed(1, 0)
+    with pytest.raises(L.PmpError, match="share"):
+        L.run_multi([a, b], 10)
+    b.close(); a.close()
