@@ -174,8 +174,9 @@ def main():
     x, y = synthetic(n_global)
     xp, yp = torch.from_numpy(x).pin_memory().numpy(), torch.from_numpy(y).pin_memory().numpy()     # pinned host buffers for the e2e arm
 
-    # N = 1: the chains share one cooperative kernel.  N > 1: every chain's data are sharded over the ranks and the chains run on
-    # separate streams / NCCL communicators, so one chain's all-reduce and acceptance overlap the other chains' sweeps.
+    # N = 1: the chains share one cooperative kernel.  N > 1: every chain's data are sharded over the ranks; the same kernel runs on
+    # every GPU and exchanges the per-node integer sums through NVLink peer memory (pmp_peer_exchange_*, attached by
+    # dist.create_context); PMP_PEER_XCHG=0 falls back to one stream + NCCL communicator per chain.
     chains = max(1, min(4, args.chains))
 
     def configure(c):
@@ -206,6 +207,7 @@ def main():
         return None
 
     reset(2024)
+    fused_multi = world > 1 and chains > 1 and all(c.peers_attached for c in ctxs) and os.environ.get("PMP_PEER_XCHG", "1") != "0"
 
     def barrier():
         if world > 1:
@@ -299,9 +301,9 @@ def main():
     persistent = world == 1 and os.environ.get("PMP_PERSISTENT", "1") != "0"
     iter_s = total_s / (args.steps * iters * chains)               # seconds per chain iteration
     traffic = None
-    if chains > 1 and world == 1:
+    if chains > 1 and (world == 1 or fused_multi):
         kernel, kernel_us, launch_flops = "chain_persistent_multi_kernel<MP> (%d chains, one launch per step)" % chains, iter_s * 1e6 * iters * chains, flops_per_iter * iters * chains
-        traffic = NCU_DRAM_BYTES_PER_LAUNCH_MULTI
+        traffic = NCU_DRAM_BYTES_PER_LAUNCH_MULTI if world == 1 else None
     elif persistent:
         kernel, kernel_us, launch_flops = "chain_persistent_kernel<MP> (one launch per step)", iter_s * 1e6 * iters, flops_per_iter * iters
         traffic = NCU_DRAM_BYTES_PER_LAUNCH
@@ -330,7 +332,9 @@ def main():
                 "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32", "data": "synthetic",
                 "iters_per_sec": iters_per_s, "us_per_iter": 1e6 / iters_per_s, "single_chain": single,
                 "config": {"workload": "simple_net linear-Gaussian multi-proposal MCMC (100000_MP.cu shape): P=1024 nodes, n=%d points, flat proposals alpha=0.01, SCALE=1000, CUDA draw rule; "
-                                       "%d independent chain(s) per GPU%s" % (n_global, chains, (" co-scheduled in one cooperative kernel (pmp_run_multi)" if world == 1 else " on separate streams and NCCL communicators, data sharded over the ranks (pmp_run_multi)") + "; iters_per_sec and value count all chains" if chains > 1 else ""),
+                                       "%d independent chain(s) per GPU%s" % (n_global, chains, (" co-scheduled in one cooperative kernel (pmp_run_multi)" if world == 1 else
+                                                                   (" co-scheduled in one cooperative kernel per GPU, data rows sharded over the ranks, per-node sums exchanged through NVLink peer memory inside the kernel (pmp_run_multi)" if fused_multi
+                                                                    else " on separate streams and NCCL communicators, data sharded over the ranks (pmp_run_multi)")) + "; iters_per_sec and value count all chains" if chains > 1 else ""),
                            "P": P_NODES, "n": n_global, "chains": chains, "iters_per_step": iters, "device": info["name"],
                            "l2": "flushed (256 MB memset) between steps; inside a step the dataset is re-read from L2 by design",
                            "baseline": "reference README.md:44, V100: (33473.53 + 1099.258) us per iteration at P=1024, n=100000"},

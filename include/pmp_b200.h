@@ -165,6 +165,14 @@ int pmp_sync(pmp_ctx* ctx);
  * data without a copy; src must outlive dst's use of it).  This is the independent-repeats pattern of the reference's
  * experiments (error.py:191-213 runs 20 repeats; the ESS runs use one process per GPU). */
 int pmp_share_data(pmp_ctx* dst, pmp_ctx* src);
+/* world_size > 1: exchange of the per-node integer sums through NVLink peer memory INSIDE the chain kernel instead of an NCCL
+ * call between kernels.  pmp_peer_exchange_handle allocates this rank's exchange buffer and returns its 64-byte CUDA IPC
+ * handle; the caller gathers the handles of all ranks (any transport) and passes them, rank-major, to pmp_peer_exchange_attach.
+ * With the peers attached pmp_run_multi runs the sharded chains in ONE cooperative kernel per GPU: sweep on the local shard,
+ * partial sums stored straight into the peers' buffers, acceptance replicated.  Without it pmp_run_multi falls back to one
+ * stream + NCCL communicator per chain.  Call both on every rank, for every ctx, in the same order. */
+int pmp_peer_exchange_handle(pmp_ctx* ctx, void* out64);
+int pmp_peer_exchange_attach(pmp_ctx* ctx, const void* handles, int n_ranks);
 int pmp_run_multi(pmp_ctx** ctxs, int n_ctx, int64_t iters, int sync);
 int pmp_run_multi_timed(pmp_ctx** ctxs, int n_ctx, int64_t iters, float* total_ms);   /* CUDA events around the joint kernel; blocking */
 /* Copy out the rows recorded since the last pmp_trace_config / pmp_trace_reset (blocking); any pointer may be NULL. */

@@ -26,6 +26,7 @@ EXPORTS = [
     "pmp_run_timed", "pmp_launch_count", "pmp_fp32_peak", "pmp_l2_flush", "pmp_chains_create", "pmp_chains_run",
     "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
     "pmp_stream_normals", "pmp_time_sweep", "pmp_share_data", "pmp_run_multi", "pmp_run_multi_timed",
+    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach",
 ]
 
 
@@ -107,6 +108,8 @@ def load():
     L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_share_data.argtypes = [vp, vp]
+    L.pmp_peer_exchange_handle.argtypes = [vp, vp]
+    L.pmp_peer_exchange_attach.argtypes = [vp, vp, i32]
     L.pmp_run_multi.argtypes = [ctypes.POINTER(vp), i32, i64, i32]
     L.pmp_run_multi_timed.argtypes = [ctypes.POINTER(vp), i32, i64, ctypes.POINTER(ctypes.c_float)]
     if L.pmp_abi_version() != 1:
@@ -161,6 +164,7 @@ class Context:
         uid = ctypes.create_string_buffer(bytes(nccl_unique_id), 128) if nccl_unique_id is not None else None
         self._chk(self.L.pmp_create(ctypes.byref(self.h), device, world_size, rank, uid))
         self.world_size, self.rank, self.device = world_size, rank, device
+        self.peers_attached = False
         self.cfg = None
         self.P = 0
 
@@ -275,6 +279,17 @@ class Context:
 
     def sync(self):
         self._chk(self.L.pmp_sync(self.h))
+
+    def peer_exchange_handle(self):
+        """64-byte CUDA IPC handle of this rank's exchange buffer (world_size > 1)."""
+        buf = ctypes.create_string_buffer(64)
+        self._chk(self.L.pmp_peer_exchange_handle(self.h, buf))
+        return buf.raw
+
+    def peer_exchange_attach(self, handles):
+        """handles: the 64-byte handles of all ranks, rank-major (bytes of length 64 * world_size)."""
+        self._chk(self.L.pmp_peer_exchange_attach(self.h, ctypes.c_char_p(bytes(handles)), len(handles) // 64))
+        self.peers_attached = True
 
     def share_data_from(self, owner):
         """Alias `owner`'s device copy of the linear-Gaussian data (no copy); `owner` must stay alive while this ctx uses it."""

@@ -19,10 +19,70 @@ namespace pmp {
 
 constexpr int PERSIST_MAX_CHAINS = 4;
 
+constexpr int PEER_MAX_WORLD = 8;
+
+// Cross-GPU exchange of one chain's per-node integer sums over NVLink peer memory (world_size > 1; data rows sharded).
+// Every rank owns a buffer  sums[2][world][MAX_NODES] u64  +  flags[world] u64  that its peers have mapped with CUDA IPC.
+// Iteration e (a launch-independent, monotone count): rank `me` stores its P partial sums into slot [e & 1][me] of EVERY
+// peer's buffer, fences at system scope, then releases flags[me] = e + 1 on every peer; it then waits until its own
+// flags[r] >= e + 1 for all r, adds the world partial vectors (integers: the total is bit-identical on every rank and for
+// any world size) and goes on with the replicated acceptance.  Two slots suffice: a peer can only write iteration e + 2
+// after it has received this rank's e + 1 sums, which are sent after the e sums have been read.
+struct PeerXchg {
+    unsigned long long* local;                 // this rank's buffer
+    unsigned long long* peer[PEER_MAX_WORLD];  // peer[r]: rank r's buffer mapped here (peer[me] = local)
+    int world, me;
+    unsigned long long base;                   // exchange count of this chain before this launch
+};
+__host__ __device__ inline size_t peer_xchg_words() { return (size_t)2 * PEER_MAX_WORLD * MAX_NODES + PEER_MAX_WORLD; }
+__host__ __device__ inline size_t peer_flag_offset() { return (size_t)2 * PEER_MAX_WORLD * MAX_NODES; }
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+// Executed by the whole acceptance CTA once the local sweep CTAs have arrived: acc[p] := sum over ranks of their acc[p].
+__device__ __forceinline__ void peer_allreduce_acc(const PeerXchg& x, unsigned long long* acc, int P, int it) {
+    const int tid = threadIdx.x;
+    const unsigned long long e = x.base + (unsigned long long)it;
+    const size_t slot = (size_t)(e & 1ull) * PEER_MAX_WORLD * MAX_NODES;
+    unsigned long long q[LEAN_K];
+#pragma unroll
+    for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? __ldcg(acc + p) : 0ull; }
+    for (int r = 0; r < x.world; ++r) {
+        if (r == x.me) continue;
+        unsigned long long* dst = x.peer[r] + slot + (size_t)x.me * MAX_NODES;
+#pragma unroll
+        for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; if (p < P) st_relaxed_sys_u64(dst + p, q[k]); }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < x.world && tid != x.me) {
+        st_release_sys_u64(x.peer[tid] + peer_flag_offset() + x.me, e + 1ull);
+        const unsigned long long* f = x.local + peer_flag_offset() + tid;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys_u64(f) < e + 1ull)
+            if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) __trap();     // a peer that never shows up must not hang the GPU
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LEAN_K; ++k) {
+        const int p = tid + k * ACCEPT_THREADS;
+        if (p < P) {
+            unsigned long long sum = q[k];
+            for (int r = 0; r < x.world; ++r) if (r != x.me) sum += ld_relaxed_sys_u64(x.local + slot + (size_t)r * MAX_NODES + p);
+            acc[p] = sum;       // read back by the same thread in lean_crit
+        }
+    }
+}
+
 struct PersistChain {
     SweepArgs sw;
     AcceptFastArgs fa;
     PersistSync* sync;
+    PeerXchg xchg;             // world == 1: unused
 };
 
 struct PersistMultiArgs {
@@ -30,11 +90,12 @@ struct PersistMultiArgs {
     int n_chains;
     int iters;
     int max_chunks;
+    int n_accept;              // acceptance CTAs: min(K, 2) on one GPU, K when the sums are exchanged with peers
 };
 
 __device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(PERSIST_THREADS / 2) : "memory"); }
 
-// Roles.  CTAs [0, n_sweep) sweep; the last n_accept = min(K, 2) CTAs accept (acceptance CTA a serves chains a, a+2, ...).
+// Roles.  CTAs [0, n_sweep) sweep; the last n_accept CTAs accept (acceptance CTA a serves chains a, a + n_accept, ...).
 // A sweep CTA is split into two independent halves of 512 threads (16 warps each, private named barrier): half h serves chains
 // h, h+2, ...  While one half waits for its chain's acceptance, reads its nodes or flushes its sums — all L2 round trips — the
 // other half's packed-FMA loop has the SM's FP32 pipe to itself, so the pipe only idles when BOTH halves are between sweeps.
@@ -44,7 +105,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
     extern __shared__ __align__(16) unsigned char dsm[];
     const int tid = threadIdx.x;
     const int K = pa.n_chains;
-    const int n_accept = K < 2 ? 1 : 2;
+    const int n_accept = pa.n_accept;
     const int n_sweep = gridDim.x - n_accept;
 
     if ((int)blockIdx.x >= n_sweep) {
@@ -59,6 +120,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 lean_pre<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
                 if (tid == 0) spin_until_ge(&pa.ch[c].sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
                 __syncthreads();
+                if (pa.ch[c].xchg.world > 1) peer_allreduce_acc(pa.ch[c].xchg, fa.base.acc, fa.base.P, it);
                 lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
                 __threadfence();
                 __syncthreads();

@@ -119,6 +119,12 @@ struct pmp_ctx {
     // FC model
     void* fc = nullptr;
 
+    // peer-memory exchange of the per-node sums (world > 1, pmp_peer_exchange_*): own buffer + the peers' buffers mapped with CUDA IPC
+    unsigned long long* d_xchg = nullptr;
+    unsigned long long* peer_xchg[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool peers_attached = false;
+    unsigned long long xchg_count = 0;   // exchanges done so far (identical on every rank: SPMD call sequence)
+
     // MP kernel term for long parameter vectors (pmp_large_dim_kernel_term)
     float* d_kt_s1 = nullptr; double* d_kt_dj2 = nullptr; double* d_kt_dot = nullptr; long long kt_dim_cap = 0;
 };

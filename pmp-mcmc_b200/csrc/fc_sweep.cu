@@ -249,6 +249,10 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtenso
     asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
@@ -274,7 +278,9 @@ struct Gemm2Args {
     int nb;                   // nodes in this batch
     const float* bias;        // [nb, bias_stride] (already offset to this layer)
     int bias_stride;
-    __nv_bfloat16* out;       // RELU_SPLIT: next layer's A' [nb, M, 2*n_total]
+    int a_tiled;              // 1: A is tile-major [nb][M/128][2*Kpad/64][128][64] (written by a RELU_SPLIT epilogue): every TMA box is one contiguous 16 KB block
+    int mb128;                // number of 128-row blocks (M rounded up)
+    __nv_bfloat16* out;       // RELU_SPLIT: next layer's A', tile-major [nb][mb128][2*n_total/64][128][64]
     const float* theta;       // L4_NLL: node parameters (float32, torch order) of the first node of the batch
     long long theta_stride;
     const int* labels;        // L4_NLL: [M]
@@ -332,8 +338,13 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                     const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                    tma_load_3d_2sm(st, &tmA, lbar, kb * BK, row0, g.a_shared ? 0 : batch);
-                    tma_load_3d_2sm(st + A_BYTES, &tmA, lbar, g.Kpad + kb * BK, row0, g.a_shared ? 0 : batch);
+                    if (g.a_tiled) {
+                        tma_load_5d_2sm(st, &tmA, lbar, 0, 0, kb, m_blk * 2 + (int)rank, batch);
+                        tma_load_5d_2sm(st + A_BYTES, &tmA, lbar, 0, 0, num_k + kb, m_blk * 2 + (int)rank, batch);
+                    } else {
+                        tma_load_3d_2sm(st, &tmA, lbar, kb * BK, row0, g.a_shared ? 0 : batch);
+                        tma_load_3d_2sm(st + A_BYTES, &tmA, lbar, g.Kpad + kb * BK, row0, g.a_shared ? 0 : batch);
+                    }
                     tma_load_3d_2sm(st + 2 * A_BYTES, &tmB, lbar, kb * BK, col0, batch);
                     tma_load_3d_2sm(st + 2 * A_BYTES + B_BYTES, &tmB, lbar, g.Kpad + kb * BK, col0, batch);
                 }
@@ -390,8 +401,11 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * CH);
             if (EPI == EPI2_RELU_SPLIT) {
                 const float* bias = g.bias + (long long)batch * g.bias_stride + n_blk * BN + chalf * CH;
-                const long long ldo = 2ll * g.n_total;
-                __nv_bfloat16* orow = g.out + ((long long)batch * g.M + row) * ldo + n_blk * BN + chalf * CH;
+                // tile-major output: [batch][128-row block][k-tile of 64 columns (h tiles, then l tiles)][row][64]
+                const int kt_half = g.n_total / 64;
+                const long long blk = (long long)batch * g.mb128 + (m_blk * 2 + (int)rank);
+                __nv_bfloat16* oblk = g.out + blk * (2ll * kt_half) * (128 * 64) + (long long)lrow * 64;
+                const int col0 = n_blk * BN + chalf * CH;
 #pragma unroll 1
                 for (int cc = 0; cc < CH / 32; ++cc) {
                     uint32_t v[32];
@@ -406,8 +420,9 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         hp[i] = pack_bf16x2(h0, h1); lp[i] = pack_bf16x2(l0, l1);
                     }
                     if (row < g.M) {
-                        uint4* d0 = reinterpret_cast<uint4*>(orow + cc * 32);
-                        uint4* d1 = reinterpret_cast<uint4*>(orow + g.n_total + cc * 32);
+                        const int col = col0 + cc * 32, kt = col >> 6, cin = col & 63;
+                        uint4* d0 = reinterpret_cast<uint4*>(oblk + (long long)kt * (128 * 64) + cin);
+                        uint4* d1 = reinterpret_cast<uint4*>(oblk + (long long)(kt_half + kt) * (128 * 64) + cin);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             d0[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
@@ -607,6 +622,20 @@ static int make_map(CUtensorMap* m, void* base, long long K3, long long rows, lo
     return PMP_OK;
 }
 
+// bf16 tile-major activations [batch][mb128][kt2 = 2*N/64][128][64]; box = one 128 x 64 tile (16 KB contiguous), 128-byte swizzle
+static int make_map_tiled(CUtensorMap* m, void* base, long long kt2, long long mb128, long long batch) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return PMP_ERR_CUDA; }
+    cuuint64_t dims[5] = {64, 128, (cuuint64_t)kt2, (cuuint64_t)mb128, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {128, 16384, 16384ull * (cuuint64_t)kt2, 16384ull * (cuuint64_t)kt2 * (cuuint64_t)mb128};
+    cuuint32_t box[5] = {64, 128, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (tile-major) failed (%d) for [%lld,%lld,%lld]", (int)r, batch, mb128, kt2); return PMP_ERR_CUDA; }
+    return PMP_OK;
+}
+
 template <int BN, int EPI> static size_t gemm_smem() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024; }
 
 template <int BN, int EPI, int NSTAGE>
@@ -688,14 +717,18 @@ int pmp_set_data_fc(pmp_ctx* c, const float* X, const int64_t* labels, int64_t n
         PMP_CUDA(cudaMalloc((void**)&s->w2, (size_t)nb * H2 * 2 * H1 * 2));
         PMP_CUDA(cudaMalloc((void**)&s->w3, (size_t)nb * H3 * 2 * H2 * 2));
         PMP_CUDA(cudaMalloc((void**)&s->bias, (size_t)nb * (H1 + H2 + H3 + NCLS_PAD) * sizeof(float)));
-        PMP_CUDA(cudaMalloc((void**)&s->a2, (size_t)nb * n_local * 2 * H1 * 2));
-        PMP_CUDA(cudaMalloc((void**)&s->a3, (size_t)nb * n_local * 2 * H2 * 2));
+        const long long mb128 = (n_local + 127) / 128;
+        PMP_CUDA(cudaMalloc((void**)&s->a2, (size_t)nb * mb128 * 128 * 2 * H1 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->a3, (size_t)nb * mb128 * 128 * 2 * H2 * 2));
+        PMP_CUDA(cudaMemsetAsync(s->a2, 0, (size_t)nb * mb128 * 128 * 2 * H1 * 2, c->stream));     // rows >= n of the last block are never written
+        PMP_CUDA(cudaMemsetAsync(s->a3, 0, (size_t)nb * mb128 * 128 * 2 * H2 * 2, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
         int rc2;
         if ((rc2 = make_map(&s->tmX, s->xs, 2 * D_IN_PAD, n_local, 1, BM))) return rc2;
         if ((rc2 = make_map(&s->tmW1, s->w1, 2 * D_IN_PAD, H1, nb, 128))) return rc2;     // each CTA of a pair loads half of the 256 weight rows
-        if ((rc2 = make_map(&s->tmA2, s->a2, 2 * H1, n_local, nb, BM))) return rc2;
+        if ((rc2 = make_map_tiled(&s->tmA2, s->a2, 2 * H1 / 64, mb128, nb))) return rc2;
         if ((rc2 = make_map(&s->tmW2, s->w2, 2 * H1, H2, nb, 128))) return rc2;
-        if ((rc2 = make_map(&s->tmA3, s->a3, 2 * H2, n_local, nb, BM))) return rc2;
+        if ((rc2 = make_map_tiled(&s->tmA3, s->a3, 2 * H2 / 64, mb128, nb))) return rc2;
         if ((rc2 = make_map(&s->tmW3, s->w3, 2 * H2, H3, nb, 64))) return rc2;
         return PMP_OK;
     }
@@ -740,11 +773,12 @@ int pmp_fc_loglik(pmp_ctx* c) {
             t = (long long)nb * bias_stride;     gather_bias_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, THETA_DIM, s->bias, nb);
             c->launches += 4;
             PMP_CUDA(cudaGetLastError());
-            Gemm2Args g1{M, D_IN_PAD, 1, H1, nb, s->bias, bias_stride, s->a2, nullptr, 0, nullptr, nullptr};
+            const int mb128 = (M + 127) / 128;
+            Gemm2Args g1{M, D_IN_PAD, 1, H1, nb, s->bias, bias_stride, 0, mb128, s->a2, nullptr, 0, nullptr, nullptr};
             if ((rc = launch_gemm2<256, EPI2_RELU_SPLIT, 3>(c, s->tmX, s->tmW1, g1))) return rc;
-            Gemm2Args g2{M, H1, 0, H2, nb, s->bias + H1, bias_stride, s->a3, nullptr, 0, nullptr, nullptr};
+            Gemm2Args g2{M, H1, 0, H2, nb, s->bias + H1, bias_stride, 1, mb128, s->a3, nullptr, 0, nullptr, nullptr};
             if ((rc = launch_gemm2<256, EPI2_RELU_SPLIT, 3>(c, s->tmA2, s->tmW2, g2))) return rc;
-            Gemm2Args g3{M, H2, 0, H3, nb, s->bias + H1 + H2, bias_stride, nullptr, th, THETA_DIM, s->labels, s->loss + p0};
+            Gemm2Args g3{M, H2, 0, H3, nb, s->bias + H1 + H2, bias_stride, 1, mb128, nullptr, th, THETA_DIM, s->labels, s->loss + p0};
             if ((rc = launch_gemm2<128, EPI2_L4_NLL, 4>(c, s->tmA3, s->tmW3, g3))) return rc;
             continue;
         }

@@ -12,6 +12,8 @@
 #include "chain_persistent.cuh"
 #include "chain_persistent_tc.cuh"
 #include "chain_persistent_multi.cuh"
+
+extern "C" int pmp_fc_loglik(pmp_ctx* c);   // fc_sweep.cu
 #include "common.cuh"
 #include "sweep_linear.cuh"
 #include "sweep_linear_tc.cuh"
@@ -237,10 +239,11 @@ static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sw
         return PMP_OK;
     }
     if ((rc = launch_propose(c))) return rc;
-    if (c->cfg.target == PMP_TARGET_FC || c->cfg.target == PMP_TARGET_EXTERNAL) {
+    if (c->cfg.target == PMP_TARGET_EXTERNAL) {
         set_error("pmp_run: target %d needs host-driven log-targets (use pmp_propose / pmp_write_logtarget / pmp_accept)", c->cfg.target);
         return PMP_ERR_UNSUPPORTED;
     }
+    if (c->cfg.target == PMP_TARGET_FC && (rc = pmp_fc_loglik(c))) return rc;     // GEMM chain + all-reduce of the integer loss sums, all on the ctx stream
     if ((rc = launch_accept(c, 0, 0, 1, nullptr))) return rc;
     c->host_iter++;
     return PMP_OK;
@@ -332,6 +335,8 @@ int pmp_destroy(pmp_ctx* c) {
     pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     if (c->data_borrowed) { c->d_x = nullptr; c->d_y = nullptr; c->d_bimg = nullptr; }     // owned by another ctx (pmp_share_data)
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) if (c->peer_xchg[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_xchg[r]);
+    if (c->d_xchg) cudaFree(c->d_xchg);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
                     c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_bimg, c->d_kt_s1, c->d_kt_dj2, c->d_kt_dot};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -753,7 +758,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
         rc = try_run_persistent(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK;
     }
     int64_t done = 0;
-    if (GI > 1 && iters >= GI) {
+    if (GI > 1 && iters >= GI && c->cfg.target != PMP_TARGET_FC) {     // FC iterations are milliseconds of GEMMs: nothing to gain from a graph
         if (!c->graph_exec || c->graph_iters != GI) {
             drop_graph(c);
             cudaGraph_t graph;
@@ -837,17 +842,21 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     pmp_ctx* c0 = cs[0];
     PMP_REQUIRE(c0 && c0->configured, "ctx 0 not configured");
     if (c0->world > 1) {
+        bool fused = env_int("PMP_PEER_XCHG", 1) != 0 && c0->world <= PEER_MAX_WORLD;
         for (int k = 0; k < K; ++k) {
             PMP_REQUIRE(cs[k] && cs[k]->configured && cs[k]->device == c0->device && cs[k]->world == c0->world && cs[k]->rank == c0->rank, "ctx %d: not configured or another rank / device", k);
             for (int j = 0; j < k; ++j) PMP_REQUIRE(cs[j] != cs[k], "ctx %d given twice", k);
+            pmp_ctx* c = cs[k];
+            fused = fused && c->peers_attached && c->cfg.target == PMP_TARGET_LINEAR_GAUSS && lean_accept_ok(c) && !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) &&
+                    c->P == c0->P && c->cfg.algo == c0->cfg.algo && c->d_x == c0->d_x && c->n_local == c0->n_local && c->n_global == c0->n_global;
         }
-        return run_multi_streams(cs, K, iters, ev_begin, ev_end);
+        if (!fused) return run_multi_streams(cs, K, iters, ev_begin, ev_end);
     }
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
         PMP_REQUIRE(c && c->configured, "ctx %d not configured", k);
         for (int j = 0; j < k; ++j) PMP_REQUIRE(cs[j] != c, "ctx %d given twice", k);
-        PMP_REQUIRE(c->device == c0->device && c->world == 1, "co-scheduled chains: one device, world_size 1");
+        PMP_REQUIRE(c->device == c0->device && c->world == c0->world, "co-scheduled chains: one device, one world");
         PMP_REQUIRE(c->cfg.target == PMP_TARGET_LINEAR_GAUSS && lean_accept_ok(c) && !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL),
                     "co-scheduled chains need the linear-Gaussian target with a device-resident acceptance rule (MP / PSP / TABLE quirk), P <= %d", LEAN_MAX_P);
         PMP_REQUIRE(c->P == c0->P && c->cfg.algo == c0->cfg.algo && c->cfg.dim == c0->cfg.dim, "ctx %d: P / algo differ from ctx 0", k);
@@ -855,7 +864,8 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
                     "ctx %d does not share ctx 0's data (pmp_share_data)", k);
     }
     PMP_CUDA(cudaSetDevice(c0->device));
-    const int G = c0->sm_count, n_sweep = G - (K < 2 ? 1 : 2);     // one acceptance CTA per chain parity
+    const int n_accept = c0->world > 1 ? K : (K < 2 ? 1 : 2);      // one acceptance CTA per chain parity; per chain when the sums cross NVLink
+    const int G = c0->sm_count, n_sweep = G - n_accept;
     const long long nchunks = (c0->n_local + CHUNK - 1) / CHUNK;
     PMP_REQUIRE(nchunks > 0 && n_sweep >= 1, "no data");
     const int ntiles = (c0->P + PERSIST_PT - 1) / PERSIST_PT;
@@ -878,9 +888,12 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
         aa.dbg = nullptr;
         pa.ch[k].fa = AcceptFastArgs{aa, c->d_z, 1, gen};
         pa.ch[k].sync = reinterpret_cast<PersistSync*>(c->d_psync);
+        pa.ch[k].xchg.world = c->world; pa.ch[k].xchg.me = c->rank; pa.ch[k].xchg.local = c->d_xchg; pa.ch[k].xchg.base = c->xchg_count;
+        for (int r = 0; r < PEER_MAX_WORLD; ++r) pa.ch[k].xchg.peer[r] = c->peer_xchg[r];
+        if (c->world > 1) c->xchg_count += (unsigned long long)iters;
         PMP_CUDA(cudaStreamSynchronize(c->stream));                // everything queued on this chain's own stream is done before the joint launch
     }
-    pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks;
+    pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks; pa.n_accept = n_accept;
     void* kargs[] = {&pa};
     const void* fn;
     switch (c0->cfg.algo) {
@@ -925,6 +938,38 @@ int pmp_run_multi_timed(pmp_ctx** ctxs, int n_ctx, int64_t iters, float* total_m
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
+}
+
+int pmp_peer_exchange_handle(pmp_ctx* c, void* out64) {
+    PMP_REQUIRE(c && out64, "bad arguments");
+    PMP_REQUIRE(c->world > 1 && c->world <= PEER_MAX_WORLD, "peer exchange needs 2..%d ranks (world_size %d)", PEER_MAX_WORLD, c->world);
+    PMP_CUDA(cudaSetDevice(c->device));
+    if (!c->d_xchg) {
+        PMP_CUDA(cudaMalloc((void**)&c->d_xchg, peer_xchg_words() * sizeof(unsigned long long)));
+        PMP_CUDA(cudaMemset(c->d_xchg, 0, peer_xchg_words() * sizeof(unsigned long long)));
+    }
+    cudaIpcMemHandle_t h;
+    PMP_CUDA(cudaIpcGetMemHandle(&h, c->d_xchg));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(out64, &h, sizeof(h));
+    return PMP_OK;
+}
+
+int pmp_peer_exchange_attach(pmp_ctx* c, const void* handles, int n_ranks) {
+    PMP_REQUIRE(c && handles && n_ranks == c->world, "bad arguments (n_ranks %d, world_size %d)", n_ranks, c ? c->world : -1);
+    PMP_REQUIRE(c->d_xchg, "pmp_peer_exchange_handle first");
+    PMP_CUDA(cudaSetDevice(c->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { c->peer_xchg[r] = c->d_xchg; continue; }
+        if (c->peer_xchg[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        PMP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_xchg[r] = (unsigned long long*)p;
+    }
+    c->peers_attached = true;
+    return PMP_OK;
 }
 
 int pmp_sync(pmp_ctx* c) {

@@ -49,7 +49,23 @@ def create_context(device=None):
     if td.get_backend() == "nccl":
         t = t.cuda(dev)
     td.broadcast(t, src=0)
-    return _lib.Context(device=dev, world_size=ws, rank=rank, nccl_unique_id=t.cpu().numpy().tobytes())
+    ctx = _lib.Context(device=dev, world_size=ws, rank=rank, nccl_unique_id=t.cpu().numpy().tobytes())
+    if os.environ.get("PMP_PEER_XCHG", "1") != "0" and ws <= 8 and hasattr(ctx, "peer_exchange_handle"):
+        attach_peers(ctx, dev)
+    return ctx
+
+
+def attach_peers(ctx, dev):
+    """All-gather the CUDA IPC handles of the ranks' exchange buffers and map the peers' buffers (NVLink peer memory): the
+    chain kernel then exchanges the per-node sums itself (pmp_run_multi) instead of calling NCCL between kernels."""
+    import torch
+    import torch.distributed as td
+    mine = torch.from_numpy(np.frombuffer(ctx.peer_exchange_handle(), dtype=np.uint8).copy())
+    if td.get_backend() == "nccl":
+        mine = mine.cuda(dev)
+    allh = [torch.empty_like(mine) for _ in range(ctx.world_size)]
+    td.all_gather(allh, mine)
+    ctx.peer_exchange_attach(b"".join(h.cpu().numpy().tobytes() for h in allh))
 
 
 def default_context():

@@ -85,11 +85,23 @@ def main():
     for c, seed in ((ctx, 99), (ctx2, 123)):
         c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
         c.trace_config(a.iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW)
-    L.run_multi([ctx, ctx2], a.iters)
-    for tag, c in (("co0", ctx), ("co1", ctx2)):
-        tr = c.read_trace()
-        for k in ("state", "next", "draws", "logw"):
-            res[tag + "_" + k] = tr[k]
+    # fused: one cooperative kernel per GPU, sums exchanged through NVLink peer memory inside it; streams: NCCL between kernels
+    for mode, tags in (("1", ("co0", "co1")), ("0", ("st0", "st1"))):
+        os.environ["PMP_PEER_XCHG"] = mode
+        for c, seed in ((ctx, 99), (ctx2, 123)):
+            c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
+            c.trace_config(a.iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW)
+        L.run_multi([ctx, ctx2], a.iters)
+        for tag, c in zip(tags, (ctx, ctx2)):
+            tr = c.read_trace()
+            t = torch.from_numpy(tr["draws"].copy()).cuda()
+            ref = t.clone(); td.broadcast(ref, src=0)
+            assert torch.equal(t, ref)                       # replicated acceptance: identical on every rank
+            for k in ("state", "next", "draws", "logw"):
+                res[tag + "_" + k] = tr[k]
+    os.environ["PMP_PEER_XCHG"] = "1"
+    L.run_multi([ctx, ctx2], a.iters)                       # a second fused launch continues the exchange counters
+    assert ctx.iteration() == 2 * a.iters and ctx2.iteration() == 2 * a.iters
     if rank == 0:
         np.savez(a.out, world=world, **res)
     ctx2.close()

@@ -99,3 +99,28 @@ def test_fc_host_layer(ctx):
     for cls in (fc.PMPOptimizer, fc.MPOptimizer, fc.MetropolisOptimizer):
         tr = cls(fc.unflatten(theta0), alpha=1e-4, seed=4).fit(num_steps=3)
         assert tr.shape == (3,) and np.all(np.abs(tr - 2.3102) < 2e-3)
+
+
+def test_fc_device_resident_run_equals_stepwise(ctx):
+    """pmp_run on the FC target (propose → GEMM chain → acceptance queued on the stream, no host round trip) walks the same
+    chain as the host-driven propose / loglik / accept sequence."""
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    X, y = _data(1500, seed=3)
+    theta0 = o.fc_init_theta(2)
+
+    def setup():
+        ctx.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-3, scale=10.0)
+        ctx.set_data_fc(X, y); ctx.set_state(theta0); ctx.seed(21, 0)
+    setup()
+    nxts = []
+    for _ in range(4):
+        ctx.propose(); ctx.loglik(read=False)
+        nxts.append(int(ctx.accept()[1]))
+    ref = ctx.get_state()
+    setup()
+    ctx.trace_config(4, L.TRACE_NEXT)
+    ctx.run(4)
+    tr = ctx.read_trace()
+    assert list(tr["next"]) == nxts and np.array_equal(ctx.get_state(), ref) and ctx.iteration() == 4
+    ctx.trace_config(0, 0)

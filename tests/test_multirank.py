@@ -60,7 +60,7 @@ def test_sharded_chain_equals_single_gpu_chain(tmp_path):
             for k in ("state", "next", "draws", "logw"):      # integer-exact partial sums → identical bits at any GPU count
                 assert np.array_equal(tr[k], g[name + "_" + k]), (name, k)
         # two sharded chains overlapped on two streams / communicators equal their solo single-GPU runs
-        for tag, seed in (("co0", 99), ("co1", 123)):
+        for tag, seed in (("co0", 99), ("co1", 123), ("st0", 99), ("st1", 123)):
             c.configure(0, b=256, depth=1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.02, scale=1000.0)
             c.set_data_linear(x, y)
             c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
