@@ -44,9 +44,9 @@ UNIT = "proposal-evals/s"
 BASELINE_EVALS_PER_S = 1024 / ((33473.53 + 1099.258) * 1e-6)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full: the dataset is read from HBM once per launch and
 # then lives in shared memory.  Single chain: profiles/r1b_chain_persistent_ncu_full_summary.txt (50-iteration launch);
-# co-scheduled chains: profiles/r1c_chain_persistent_multi_ncu_full_summary.txt (4 chains x 50 iterations).
+# co-scheduled chains: profiles/r1c_chain_persistent_multi_ncu_full_summary.txt (4 chains x 1000 iterations: the launch the bench times).
 NCU_DRAM_BYTES_PER_LAUNCH = 914944 + 2304
-NCU_DRAM_BYTES_PER_LAUNCH_MULTI = None
+NCU_DRAM_BYTES_PER_LAUNCH_MULTI = 1004288 + 58112
 
 
 def synthetic(n, seed=0):
@@ -177,7 +177,7 @@ def main():
     # N = 1: the chains share one cooperative kernel.  N > 1: every chain's data are sharded over the ranks; the same kernel runs on
     # every GPU and exchanges the per-node integer sums through NVLink peer memory (pmp_peer_exchange_*, attached by
     # dist.create_context); PMP_PEER_XCHG=0 falls back to one stream + NCCL communicator per chain.
-    chains = max(1, min(4, args.chains))
+    chains = max(1, min(8, args.chains))
 
     def configure(c):
         c.configure(L.TREE_FLAT, b=P_NODES, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=ALPHA, scale=SCALE)

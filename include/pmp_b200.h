@@ -158,7 +158,7 @@ int pmp_run(pmp_ctx* ctx, int64_t iters, int sync);
 int pmp_sync(pmp_ctx* ctx);
 
 /* Co-scheduled chains.  A single chain is a dependency loop (sweep on all SMs → acceptance on one → next sweep), so the sweep
- * SMs idle while their chain is being accepted.  pmp_run_multi runs n_ctx (<= 4) INDEPENDENT chains — one pmp_ctx each: own
+ * SMs idle while their chain is being accepted.  pmp_run_multi runs n_ctx (<= 8) INDEPENDENT chains — one pmp_ctx each: own
  * state, Philox key, trace — in one cooperative kernel, sweeping chain B while chain A is accepted.  Each chain's results are
  * bit-identical to the same ctx run alone with pmp_run.  Requirements: one device, world_size 1, linear-Gaussian target, the
  * same tree / algo in every ctx, and every ctx sharing ctxs[0]'s device copy of the data (pmp_share_data: dst aliases src's
@@ -179,6 +179,11 @@ int pmp_run_multi_timed(pmp_ctx** ctxs, int n_ctx, int64_t iters, float* total_m
 int pmp_read_trace(pmp_ctx* ctx, int64_t max_iters, float* state, int32_t* next, int32_t* draws, float* samples,
                    double* logw, int64_t* n_recorded);
 int pmp_trace_reset(pmp_ctx* ctx);
+/* Diagnostics of the recorded STATE trace, reduced on the device (blocking): per coordinate mean[dim], variance[dim] (1/n) and
+ * autocovariances acov[(max_lag+1), dim] (acov[k,j] = 1/n sum_t (x_t - m)(x_{t+k} - m)); the mean squared jump distance; the fraction
+ * of iterations whose accepted node is not node 0 (-1 without a NEXT trace).  ESS/s and MSJD/s are the reference's headline
+ * comparison (README.md:56), computed offline there from the dumped sample files.  Any output pointer may be NULL. */
+int pmp_trace_diagnostics(pmp_ctx* ctx, int max_lag, double* mean, double* var, double* acov, double* msjd, double* move_rate, int64_t* n_rows);
 
 /* Timing helpers for bench.py: CUDA events on the ctx stream. pmp_run_timed = pmp_run + device time of the whole
  * region; sweep_ms (nullable) = summed device time of the sweep kernel alone over the region. */

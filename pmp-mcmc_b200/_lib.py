@@ -26,7 +26,7 @@ EXPORTS = [
     "pmp_run_timed", "pmp_launch_count", "pmp_fp32_peak", "pmp_l2_flush", "pmp_chains_create", "pmp_chains_run",
     "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
     "pmp_stream_normals", "pmp_time_sweep", "pmp_share_data", "pmp_run_multi", "pmp_run_multi_timed",
-    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach",
+    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach", "pmp_trace_diagnostics",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
     L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_share_data.argtypes = [vp, vp]
+    L.pmp_trace_diagnostics.argtypes = [vp, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     L.pmp_peer_exchange_handle.argtypes = [vp, vp]
     L.pmp_peer_exchange_attach.argtypes = [vp, vp, i32]
     L.pmp_run_multi.argtypes = [ctypes.POINTER(vp), i32, i64, i32]
@@ -319,6 +320,15 @@ class Context:
         r = rec.value
         cut = lambda a: a[:r] if a is not None else None
         return {"n": r, "state": cut(state), "next": cut(nxt), "draws": cut(draws), "samples": cut(samples), "logw": cut(logw)}
+
+    def trace_diagnostics(self, max_lag=256):
+        """Device reduction of the STATE trace: mean, variance, autocovariances up to max_lag, MSJD, move rate."""
+        d = self.cfg.dim
+        mean, var = np.empty(d), np.empty(d)
+        acov = np.zeros((max_lag + 1, d))
+        msjd, mv, rows = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        self._chk(self.L.pmp_trace_diagnostics(self.h, max_lag, _ptr(mean), _ptr(var), _ptr(acov), ctypes.byref(msjd), ctypes.byref(mv), ctypes.byref(rows)))
+        return {"n": rows.value, "mean": mean, "var": var, "acov": acov[: min(max_lag, rows.value - 1) + 1], "msjd": msjd.value, "move_rate": mv.value}
 
     def run_timed(self, iters, sweep=False):
         total, sw = ctypes.c_float(), ctypes.c_float()

@@ -17,62 +17,71 @@
 
 namespace pmp {
 
-constexpr int PERSIST_MAX_CHAINS = 4;
+constexpr int PERSIST_MAX_CHAINS = 8;
 
 constexpr int PEER_MAX_WORLD = 8;
 
 // Cross-GPU exchange of one chain's per-node integer sums over NVLink peer memory (world_size > 1; data rows sharded).
-// Every rank owns a buffer  sums[2][world][MAX_NODES] u64  +  flags[world] u64  that its peers have mapped with CUDA IPC.
-// Iteration e (a launch-independent, monotone count): rank `me` stores its P partial sums into slot [e & 1][me] of EVERY
-// peer's buffer, fences at system scope, then releases flags[me] = e + 1 on every peer; it then waits until its own
-// flags[r] >= e + 1 for all r, adds the world partial vectors (integers: the total is bit-identical on every rank and for
-// any world size) and goes on with the replicated acceptance.  Two slots suffice: a peer can only write iteration e + 2
-// after it has received this rank's e + 1 sums, which are sent after the e sums have been read.
+// Every rank owns a buffer  slots[2][world][MAX_NODES] x 16 bytes  that its peers have mapped with CUDA IPC.  The exchange is
+// flag-in-data (the scheme of NCCL's LL protocol): a 64-bit sum travels as two 8-byte words {low 32 bits | tag << 32},
+// {high 32 bits | tag << 32}, tag = exchange count + 1.  8-byte stores are single-copy atomic, so a word whose tag matches is
+// complete by itself: no fence, no separate flag, no second NVLink trip.  Exchange e (a launch-independent, monotone
+// count): rank `me` stores its P tagged sums into slot [e & 1][me] of EVERY peer's buffer, then every thread polls its own
+// nodes in slot [e & 1][r] of the local buffer until both tags read e + 1, adds the world partial vectors (integers: the
+// total is bit-identical on every rank and for any world size) and goes on with the replicated acceptance.  Two slots
+// suffice: a peer can only write exchange e + 2 after it has received this rank's e + 1 sums, which are sent after the e
+// sums have been read; the tag of the slot's previous use (e - 1) never equals e + 1.
 struct PeerXchg {
     unsigned long long* local;                 // this rank's buffer
     unsigned long long* peer[PEER_MAX_WORLD];  // peer[r]: rank r's buffer mapped here (peer[me] = local)
     int world, me;
     unsigned long long base;                   // exchange count of this chain before this launch
 };
-__host__ __device__ inline size_t peer_xchg_words() { return (size_t)2 * PEER_MAX_WORLD * MAX_NODES + PEER_MAX_WORLD; }
-__host__ __device__ inline size_t peer_flag_offset() { return (size_t)2 * PEER_MAX_WORLD * MAX_NODES; }
+__host__ __device__ inline size_t peer_xchg_words() { return (size_t)2 * PEER_MAX_WORLD * MAX_NODES * 2; }
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 
 // Executed by the whole acceptance CTA once the local sweep CTAs have arrived: acc[p] := sum over ranks of their acc[p].
 __device__ __forceinline__ void peer_allreduce_acc(const PeerXchg& x, unsigned long long* acc, int P, int it) {
     const int tid = threadIdx.x;
     const unsigned long long e = x.base + (unsigned long long)it;
-    const size_t slot = (size_t)(e & 1ull) * PEER_MAX_WORLD * MAX_NODES;
+    const unsigned long long tag = ((e + 1ull) & 0xffffffffull) << 32;
+    const size_t slot = (size_t)(e & 1ull) * PEER_MAX_WORLD * MAX_NODES * 2;
     unsigned long long q[LEAN_K];
 #pragma unroll
     for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? __ldcg(acc + p) : 0ull; }
     for (int r = 0; r < x.world; ++r) {
         if (r == x.me) continue;
-        unsigned long long* dst = x.peer[r] + slot + (size_t)x.me * MAX_NODES;
+        unsigned long long* dst = x.peer[r] + slot + (size_t)x.me * MAX_NODES * 2;
 #pragma unroll
-        for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; if (p < P) st_relaxed_sys_u64(dst + p, q[k]); }
+        for (int k = 0; k < LEAN_K; ++k) {
+            const int p = tid + k * ACCEPT_THREADS;
+            if (p < P) st_relaxed_sys_v2(dst + 2 * p, (q[k] & 0xffffffffull) | tag, (q[k] >> 32) | tag);
+        }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < x.world && tid != x.me) {
-        st_release_sys_u64(x.peer[tid] + peer_flag_offset() + x.me, e + 1ull);
-        const unsigned long long* f = x.local + peer_flag_offset() + tid;
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned spins = 0;
-        while (ld_acquire_sys_u64(f) < e + 1ull)
-            if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) __trap();     // a peer that never shows up must not hang the GPU
-    }
-    __syncthreads();
+    const unsigned long long t0 = globaltimer_ns();
 #pragma unroll
     for (int k = 0; k < LEAN_K; ++k) {
         const int p = tid + k * ACCEPT_THREADS;
         if (p < P) {
             unsigned long long sum = q[k];
-            for (int r = 0; r < x.world; ++r) if (r != x.me) sum += ld_relaxed_sys_u64(x.local + slot + (size_t)r * MAX_NODES + p);
+            for (int r = 0; r < x.world; ++r) {
+                if (r == x.me) continue;
+                const unsigned long long* src = x.local + slot + (size_t)r * MAX_NODES * 2 + 2 * p;
+                unsigned long long lo, hi;
+                unsigned spins = 0;
+                for (;;) {
+                    ld_relaxed_sys_v2(src, lo, hi);
+                    if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+                    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) __trap();     // a peer that never shows up must not hang the GPU
+                }
+                sum += (lo & 0xffffffffull) | (hi << 32);
+            }
             acc[p] = sum;       // read back by the same thread in lean_crit
         }
     }
@@ -142,6 +151,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
     unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE) + (size_t)half * TDH * PT;   // [TDH][PT] per half
     __shared__ float sprops_all[2][PT * 3];
     __shared__ double sscl_all[2][PT];
+    __shared__ unsigned long long s_iter0[PERSIST_MAX_CHAINS];   // Philox iteration of every chain at launch, read before any acceptance can advance it
+    if (tid < K) s_iter0[tid] = __ldcg(&pa.ch[tid].sw.cnt->iteration);
     float* sprops = sprops_all[half];
     double* sscl = sscl_all[half];
 
@@ -174,23 +185,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
         __syncthreads();
     }
 
-    // this half's chains: half, half + 2 (K <= 4): Philox iteration of the chain at launch, read before any acceptance can advance it
-    unsigned long long iter0[2];
-    iter0[0] = (half < K) ? __ldcg(&pa.ch[half].sw.cnt->iteration) : 0ull;
-    iter0[1] = (half + 2 < K) ? __ldcg(&pa.ch[half + 2].sw.cnt->iteration) : 0ull;
-    bool sat0 = false, sat1 = false;
+    unsigned sat_mask = 0;
 
     for (int it = 0; it < pa.iters; ++it) {
 #pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-            const int c = half + 2 * q;
-            if (c >= K) break;
+        for (int c = half; c < K; c += 2) {                      // this half's chains: half, half + 2, ...
             const SweepArgs& a = pa.ch[c].sw;
             if (htid == 0 && it > 0) spin_until_ge(&pa.ch[c].sync->version, (unsigned)it);
             half_sync(half);
             {   // side job: this CTA's slice of the chain's NEXT-iteration normals (they depend on counters only)
                 const int zcount = P * 3, per = (zcount + n_sweep - 1) / n_sweep;
-                const unsigned long long iter = (q ? iter0[1] : iter0[0]) + (unsigned long long)it;
+                const unsigned long long iter = s_iter0[c] + (unsigned long long)it;
                 for (int k = HT - 1 - htid; k < per; k += HT) {
                     const int e = blockIdx.x * per + k;
                     if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
@@ -232,14 +237,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 }
                 half_sync(half);
             }
-            if (q) sat1 |= sat; else sat0 |= sat;
+            if (sat) sat_mask |= 1u << c;
             __threadfence();
             half_sync(half);
             if (htid == 0) atomicAdd(&pa.ch[c].sync->arrive, 1u);
         }
     }
-    if (sat0 && half < K) atomicOr(&pa.ch[half].sw.cnt->flags, 1);
-    if (sat1 && half + 2 < K) atomicOr(&pa.ch[half + 2].sw.cnt->flags, 1);
+    for (int c = 0; c < K; ++c) if (sat_mask & (1u << c)) atomicOr(&pa.ch[c].sw.cnt->flags, 1);
 }
 
 }  // namespace pmp

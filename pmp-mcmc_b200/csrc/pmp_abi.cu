@@ -249,6 +249,45 @@ static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sw
     return PMP_OK;
 }
 
+// ---- chain diagnostics over the STATE trace (ESS/s and MSJD/s are the reference's headline comparison, README:56,
+// computed offline there from the dumped samples) -------------------------------------------------------------------------------
+__global__ void diag_moments_kernel(const float* __restrict__ st, long long n, int dim, double* __restrict__ mean, double* __restrict__ var) {
+    __shared__ double red[32];
+    const int j = blockIdx.x;
+    double s = 0.0;
+    for (long long t = threadIdx.x; t < n; t += blockDim.x) s += (double)st[t * dim + j];
+    s = block_sum(s, red);
+    const double m = s / (double)n;
+    double v = 0.0;
+    for (long long t = threadIdx.x; t < n; t += blockDim.x) { const double d = (double)st[t * dim + j] - m; v = fma(d, d, v); }
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) { mean[j] = m; var[j] = v / (double)n; }
+}
+// acov[k, j] = (1/n) sum_{t < n-k} (x_t - m_j)(x_{t+k} - m_j)
+__global__ void diag_acov_kernel(const float* __restrict__ st, long long n, int dim, const double* __restrict__ mean, double* __restrict__ acov) {
+    __shared__ double red[32];
+    const int k = blockIdx.x, j = blockIdx.y;
+    const double m = mean[j];
+    double s = 0.0;
+    for (long long t = threadIdx.x; t + k < n; t += blockDim.x) s = fma((double)st[t * dim + j] - m, (double)st[(t + k) * dim + j] - m, s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) acov[(long long)k * dim + j] = s / (double)n;
+}
+// out[0] = mean squared jump distance, out[1] = fraction of iterations whose accepted node is not node 0 (-1 without a NEXT trace)
+__global__ void diag_jumps_kernel(const float* __restrict__ st, const int32_t* __restrict__ next, long long n, int dim, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0, mv = 0.0;
+    for (long long t = threadIdx.x; t + 1 < n; t += blockDim.x) {
+        double d2 = 0.0;
+        for (int j = 0; j < dim; ++j) { const double d = (double)st[(t + 1) * dim + j] - (double)st[t * dim + j]; d2 = fma(d, d, d2); }
+        s += d2;
+    }
+    if (next) for (long long t = threadIdx.x; t < n; t += blockDim.x) mv += next[t] != 0 ? 1.0 : 0.0;
+    s = block_sum(s, red);
+    mv = block_sum(mv, red);
+    if (threadIdx.x == 0) { out[0] = n > 1 ? s / (double)(n - 1) : 0.0; out[1] = next ? mv / (double)n : -1.0; }
+}
+
 }  // namespace pmp
 
 using namespace pmp;
@@ -875,7 +914,9 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     const size_t accept_smem = lean_smem_bytes(c0->P, c0->cfg.algo);
     const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
     if (smem > 200 * 1024) { set_error("co-scheduled chains: a sweep CTA's data slice (%zu bytes) does not fit shared memory", smem); return PMP_ERR_UNSUPPORTED; }
-    PersistMultiArgs pa{};
+    static PersistMultiArgs pa_storage;            // ~5 KB: more than the classic 4 KB kernel-parameter limit (CUDA >= 12.1 on sm_70+ allows 32 KB)
+    PersistMultiArgs& pa = pa_storage;
+    pa = PersistMultiArgs{};
     int rc;
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
@@ -969,6 +1010,41 @@ int pmp_peer_exchange_attach(pmp_ctx* c, const void* handles, int n_ranks) {
         c->peer_xchg[r] = (unsigned long long*)p;
     }
     c->peers_attached = true;
+    return PMP_OK;
+}
+
+int pmp_trace_diagnostics(pmp_ctx* c, int max_lag, double* mean, double* var, double* acov, double* msjd, double* move_rate, int64_t* n_rows) {
+    PMP_REQUIRE(c && c->configured, "ctx not configured");
+    PMP_REQUIRE(c->trace.state, "diagnostics need a STATE trace (pmp_trace_config with PMP_TRACE_STATE)");
+    PMP_REQUIRE(max_lag >= 0 && max_lag < 65535, "max_lag out of range");
+    PMP_CUDA(cudaSetDevice(c->device));
+    long long rows = 0;
+    PMP_CUDA(cudaMemcpyAsync(&rows, &c->d_cnt->trace_rows, sizeof(rows), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    if (rows > c->trace.capacity) rows = c->trace.capacity;
+    PMP_REQUIRE(rows >= 2, "diagnostics need at least two recorded iterations (have %lld)", rows);
+    if (max_lag >= rows) max_lag = (int)rows - 1;
+    const int dim = c->cfg.dim;
+    PMP_REQUIRE(dim <= 65535, "dim too large for the diagnostics kernels");
+    double* d = nullptr;
+    const size_t words = (size_t)2 * dim + (size_t)(max_lag + 1) * dim + 2;
+    PMP_CUDA(cudaMalloc((void**)&d, words * sizeof(double)));
+    double *d_mean = d, *d_var = d + dim, *d_acov = d + 2 * dim, *d_j = d_acov + (size_t)(max_lag + 1) * dim;
+    diag_moments_kernel<<<dim, 1024, 0, c->stream>>>(c->trace.state, rows, dim, d_mean, d_var);
+    diag_acov_kernel<<<dim3(max_lag + 1, dim), 1024, 0, c->stream>>>(c->trace.state, rows, dim, d_mean, d_acov);
+    diag_jumps_kernel<<<1, 1024, 0, c->stream>>>(c->trace.state, (c->trace.what & PMP_TRACE_NEXT) ? c->trace.next : nullptr, rows, dim, d_j);
+    c->launches += 3;
+    std::vector<double> h(words);
+    cudaError_t e = cudaMemcpyAsync(h.data(), d, words * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    PMP_CUDA(e);
+    if (mean) memcpy(mean, h.data(), dim * sizeof(double));
+    if (var) memcpy(var, h.data() + dim, dim * sizeof(double));
+    if (acov) memcpy(acov, h.data() + 2 * dim, (size_t)(max_lag + 1) * dim * sizeof(double));
+    if (msjd) *msjd = h[words - 2];
+    if (move_rate) *move_rate = h[words - 1];
+    if (n_rows) *n_rows = rows;
     return PMP_OK;
 }
 

@@ -21,14 +21,16 @@ def _configure(c, L, k):
 
 
 @pytest.mark.parametrize("name,k", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("n_chains", [1, 2, 3, 4])
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 4, 8])
 def test_co_scheduled_chains_equal_solo_chains(name, k, n_chains):
     import pmp_mcmc_b200 as pm
     from pmp_mcmc_b200 import _lib as L
     n, iters = 5000, 40
     x, y = synthetic_linear(n, seed=3)
     what = L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW
-    starts = [np.array([0.0, 0.0, 1.0], np.float32), np.array([-1.0, 2.0, 0.5], np.float32), np.array([0.5, 0.5, 2.0], np.float32), np.array([1.0, 1.0, 1.0], np.float32)]
+    rs = np.random.default_rng(17)
+    starts = [np.array([0.0, 0.0, 1.0], np.float32), np.array([-1.0, 2.0, 0.5], np.float32)] + \
+             [np.array([rs.uniform(-1, 1), rs.uniform(-1, 2), rs.uniform(0.5, 2)], np.float32) for _ in range(6)]
     solo = []
     for i in range(n_chains):
         c = pm.Context(0)
