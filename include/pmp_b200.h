@@ -60,7 +60,9 @@ typedef enum pmp_target {
     PMP_TARGET_BANANA = 2,       /* -x1^2/2 - (x2 - 2(x1^2-5))^2/2 (banana_data.ipynb cell 2), dim 2        */
     PMP_TARGET_STDNORMAL = 3,    /* log N(theta; 0, I_d) (com_dim.py:13-15 with mu=0, cov=I), any dim       */
     PMP_TARGET_FC = 4,           /* -CE(MLP 784-512-256-128-10)/loss_div (PMP_FC.py:21-44); needs set_data_fc */
-    PMP_TARGET_EXTERNAL = 5      /* log-targets supplied with pmp_write_logtarget (arbitrary loss(net) callables) */
+    PMP_TARGET_EXTERNAL = 5,     /* log-targets supplied with pmp_write_logtarget (arbitrary loss(net) callables) */
+    PMP_TARGET_GLM_LOGISTIC = 6, /* sum_i log sigmoid(s_i x_i.theta), s_i = 2 y_i - 1, theta in R^d; needs pmp_set_data_glm */
+    PMP_TARGET_GLM_GAUSS = 7     /* y_i ~ N(x_i.theta[0:d], theta[d]^2): d coefficients + sigma, dim = d + 1 (lb.py:100-108 with a d-vector covariate) */
 } pmp_target;
 
 /* Acceptance rule: how the P log-targets become log-weights. */
@@ -212,6 +214,11 @@ int pmp_chains_run_timed(pmp_ctx* ctx, int64_t iters, int record_samples, float*
 /* ---- FC model (PMP_FC.py:21-44): X [n,784] float32 row-major, labels int64; theta layout = torch parameter order
  * fc1.weight[512,784], fc1.bias[512], fc2.weight[256,512], fc2.bias, fc3.weight[128,256], fc3.bias, fc4.weight[10,128], fc4.bias. */
 int pmp_set_data_fc(pmp_ctx* ctx, const float* X, const int64_t* labels, int64_t n_local, int64_t n_offset, int64_t n_global);
+
+/* ---- d-dimensional linear / logistic regression heads (PMP_TARGET_GLM_*): X [n, d] float32 row-major, y [n] float32 ({0,1} labels
+ * for LOGISTIC, responses for GAUSS).  The P x n sweep is ONE tcgen05 GEMM [n, d] x [d, P] with a fused softplus / square epilogue
+ * and a warp-shuffle per-node reduction; shards must start at multiples of 32 rows. */
+int pmp_set_data_glm(pmp_ctx* ctx, const float* X, const float* y, int64_t n_local, int64_t n_offset, int64_t n_global, int d);
 
 #ifdef __cplusplus
 }

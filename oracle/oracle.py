@@ -497,3 +497,21 @@ def fc_loss_torch32(X, y, theta, div=10.0):
         x = F.relu(F.linear(x, W1, b1)); x = F.relu(F.linear(x, W2, b2)); x = F.relu(F.linear(x, W3, b3))
         x = F.linear(x, W4, b4)
         return float(torch.nn.CrossEntropyLoss()(x, torch.from_numpy(np.asarray(y, dtype=np.int64))) / div)
+
+
+# ---- d-dimensional GLM heads (extension of the simple-net model; no reference counterpart: plain binary64) ----
+def loglik_glm_f64(X, y, thetas, kind, scale=1.0):
+    """kind 'logistic': sum_i log sigmoid(s_i x_i.theta), s_i = 2 y_i - 1.  kind 'gauss': theta = (coefficients, sigma),
+    sum_i log N(y_i; x_i.coef, sigma^2) — lb.py:103-108 with a d-vector covariate.  Returns loglik / scale per row of thetas."""
+    X = np.asarray(X, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    th = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    out = np.empty(len(th))
+    for p, t in enumerate(th):
+        if kind == "logistic":
+            u = (2.0 * (y > 0.5) - 1.0) * (X @ t)
+            out[p] = -np.sum(np.maximum(-u, 0.0) + np.log1p(np.exp(-np.abs(u))))
+        else:
+            r = y - X @ t[:-1]
+            sg = t[-1]
+            out[p] = -0.5 * len(y) * np.log(2.0 * np.pi * sg * sg) - 0.5 * np.sum(r * r) / (sg * sg)
+    return out / scale

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(CSRC, "libpmp_b200.so")
 
 # enums of include/pmp_b200.h
 TREE_FLAT, TREE_BINARY, TREE_BARY = 0, 1, 2
-TARGET_LINEAR_GAUSS, TARGET_NORMAL1D, TARGET_BANANA, TARGET_STDNORMAL, TARGET_FC, TARGET_EXTERNAL = range(6)
+TARGET_LINEAR_GAUSS, TARGET_NORMAL1D, TARGET_BANANA, TARGET_STDNORMAL, TARGET_FC, TARGET_EXTERNAL, TARGET_GLM_LOGISTIC, TARGET_GLM_GAUSS = range(8)
 ALGO_MH, ALGO_BARKER, ALGO_MP, ALGO_PSP, ALGO_PMP, ALGO_TABLE = range(6)
 DRAW_PYTHON, DRAW_CUDA, DRAW_SINGLE = range(3)
 FLAG_QUIRK_LEVEL_MOD, FLAG_QUIRK_TABLE_CONST, FLAG_STANDARDIZE, FLAG_KERNEL_MEAN, FLAG_NO_KERNEL_TERM, FLAG_UNIFORM_PROPOSAL = 1, 2, 4, 8, 16, 32
@@ -26,7 +26,7 @@ EXPORTS = [
     "pmp_run_timed", "pmp_launch_count", "pmp_fp32_peak", "pmp_l2_flush", "pmp_chains_create", "pmp_chains_run",
     "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
     "pmp_stream_normals", "pmp_time_sweep", "pmp_share_data", "pmp_run_multi", "pmp_run_multi_timed",
-    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach", "pmp_trace_diagnostics",
+    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach", "pmp_trace_diagnostics", "pmp_set_data_glm",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
     L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_share_data.argtypes = [vp, vp]
+    L.pmp_set_data_glm.argtypes = [vp, vp, vp, i64, i64, i64, i32]
     L.pmp_trace_diagnostics.argtypes = [vp, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     L.pmp_peer_exchange_handle.argtypes = [vp, vp]
     L.pmp_peer_exchange_attach.argtypes = [vp, vp, i32]
@@ -378,6 +379,14 @@ class Context:
         out = np.empty((self._chain_iters, self.P, self.cfg.dim, self.n_chains), dtype=np.float32)
         self._chk(self.L.pmp_chains_read_samples(self.h, _ptr(out), out.size))
         return out
+
+    def set_data_glm(self, X, y, n_offset=0, n_global=None):
+        """X [n, d] float32, y [n] float32 ({0,1} labels for the logistic head, responses for the Gaussian head)."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32).reshape(-1)
+        if X.ndim != 2 or len(X) != len(y):
+            raise ValueError("X must be [n, d] and y [n]")
+        self._chk(self.L.pmp_set_data_glm(self.h, _ptr(X), _ptr(y), len(y), n_offset, len(y) if n_global is None else n_global, X.shape[1]))
 
     def set_data_fc(self, X, labels, n_offset=0, n_global=None):
         X = np.ascontiguousarray(X, dtype=np.float32).reshape(len(labels), -1)

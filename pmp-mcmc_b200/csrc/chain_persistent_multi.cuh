@@ -102,14 +102,17 @@ struct PersistMultiArgs {
     int n_accept;              // acceptance CTAs: min(K, 2) on one GPU, K when the sums are exchanged with peers
 };
 
-__device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(PERSIST_THREADS / 2) : "memory"); }
+template <int NG>
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(PERSIST_THREADS / NG) : "memory"); }
 
 // Roles.  CTAs [0, n_sweep) sweep; the last n_accept CTAs accept (acceptance CTA a serves chains a, a + n_accept, ...).
-// A sweep CTA is split into two independent halves of 512 threads (16 warps each, private named barrier): half h serves chains
-// h, h+2, ...  While one half waits for its chain's acceptance, reads its nodes or flushes its sums — all L2 round trips — the
-// other half's packed-FMA loop has the SM's FP32 pipe to itself, so the pipe only idles when BOTH halves are between sweeps.
-// The per-node sums are integers, so splitting the chunk lanes 16 + 16 instead of 32 changes no bit of the result.
-template <int ALGO>
+// A sweep CTA is split into NG (2 or 4) independent warp groups of 1024 / NG threads with private named barriers: group h serves
+// chains h, h + NG, ...  While one group waits for its chain's acceptance, reads its nodes or flushes its sums — all L2 round
+// trips — the other groups' packed-FMA loops have the SM's FP32 pipe to themselves, so the pipe only idles when ALL groups are
+// between sweeps.  NG = 4 when at least four chains are resident: on a shard of the data (world_size > 1) the sweep itself is
+// short and the per-iteration round trips dominate, so more of them must be in flight.  The per-node sums are integers, so
+// splitting the chunk lanes NG ways changes no bit of the result.
+template <int ALGO, int NG>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_kernel(const __grid_constant__ PersistMultiArgs pa) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int tid = threadIdx.x;
@@ -144,13 +147,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
 
     // ================= sweep CTAs =================
     constexpr int R = PERSIST_R, TP = PERSIST_TP, PT = PERSIST_PT;
-    constexpr int HT = PERSIST_THREADS / 2, TDH = HT / TP;                                  // threads / chunk lanes of one half
+    constexpr int HT = PERSIST_THREADS / NG, TDH = HT / TP;                                 // threads / chunk lanes of one warp group
     const SweepArgs& a0 = pa.ch[0].sw;                                                      // data, shapes: the same for every chain
     float* tile = reinterpret_cast<float*>(dsm);                                           // [max_chunks][CHUNK_STRIDE], read-only after staging
     const int half = tid / HT, htid = tid - half * HT;
     unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE) + (size_t)half * TDH * PT;   // [TDH][PT] per half
-    __shared__ float sprops_all[2][PT * 3];
-    __shared__ double sscl_all[2][PT];
+    __shared__ float sprops_all[NG][PT * 3];
+    __shared__ double sscl_all[NG][PT];
     __shared__ unsigned long long s_iter0[PERSIST_MAX_CHAINS];   // Philox iteration of every chain at launch, read before any acceptance can advance it
     if (tid < K) s_iter0[tid] = __ldcg(&pa.ch[tid].sw.cnt->iteration);
     float* sprops = sprops_all[half];
@@ -189,10 +192,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
 
     for (int it = 0; it < pa.iters; ++it) {
 #pragma unroll 1
-        for (int c = half; c < K; c += 2) {                      // this half's chains: half, half + 2, ...
+        for (int c = half; c < K; c += NG) {                     // this group's chains: group, group + NG, ...
             const SweepArgs& a = pa.ch[c].sw;
             if (htid == 0 && it > 0) spin_until_ge(&pa.ch[c].sync->version, (unsigned)it);
-            half_sync(half);
+            group_sync<NG>(half);
             {   // side job: this CTA's slice of the chain's NEXT-iteration normals (they depend on counters only)
                 const int zcount = P * 3, per = (zcount + n_sweep - 1) / n_sweep;
                 const unsigned long long iter = s_iter0[c] + (unsigned long long)it;
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                     sprops[i] = v;
                     if (j == 2) sscl[i / 3] = (node < P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
                 }
-                half_sync(half);
+                group_sync<NG>(half);
                 float b0[R], b1[R]; double scl[R]; unsigned long long accq[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) { int i = tp * R + r; b0[r] = sprops[3 * i]; b1[r] = sprops[3 * i + 1]; scl[r] = sscl[i]; accq[r] = 0ull; }
@@ -229,17 +232,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) sred[td * PT + tp * R + r] = accq[r];
-                half_sync(half);
+                group_sync<NG>(half);
                 for (int i = htid; i < PT; i += HT) {
                     unsigned long long sum = 0ull;
                     for (int k = 0; k < TDH; ++k) sum += sred[k * PT + i];
                     if (node_base + i < P && sum) atomicAdd(a.acc + node_base + i, sum);
                 }
-                half_sync(half);
+                group_sync<NG>(half);
             }
             if (sat) sat_mask |= 1u << c;
             __threadfence();
-            half_sync(half);
+            group_sync<NG>(half);
             if (htid == 0) atomicAdd(&pa.ch[c].sync->arrive, 1u);
         }
     }

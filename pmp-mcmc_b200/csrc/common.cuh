@@ -116,8 +116,9 @@ struct pmp_ctx {
     unsigned long long chain_iteration = 0;
     void* chain_scratch = nullptr;
 
-    // FC model
+    // FC model, GLM heads
     void* fc = nullptr;
+    void* glm = nullptr;
 
     // peer-memory exchange of the per-node sums (world > 1, pmp_peer_exchange_*): own buffer + the peers' buffers mapped with CUDA IPC
     unsigned long long* d_xchg = nullptr;

@@ -266,7 +266,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1 };
+enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1, EPI2_GLM = 2 };
+enum { GLM_LOGISTIC = 0, GLM_GAUSS = 1 };
+constexpr int GLM_FX_SHIFT = 24;                                 // fixed-point format of the per-node sums of the GLM heads
 constexpr int GEMM2_EPI_WARPS = 8;                               // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int GEMM2_THREADS = 64 + 32 * GEMM2_EPI_WARPS;
 
@@ -285,6 +287,12 @@ struct Gemm2Args {
     long long theta_stride;
     const int* labels;        // L4_NLL: [M]
     unsigned long long* loss; // L4_NLL: [nb] fixed-point sums
+    // GLM: columns are NODES (B = theta of all nodes, nb = 1, the launch uses a multiple of n_total / BN pairs so that a pair keeps
+    // its node block); per node sum over rows of softplus(-s_i t) (LOGISTIC) or (y_i - t)^2 (GAUSS), t = x_i . theta
+    const float* gy;          // [M] s_i = +1 / -1 (LOGISTIC) or y_i (GAUSS)
+    int glm_kind;
+    unsigned long long* glm_acc;   // [n_total] fixed-point sums
+    double glm_sat;           // per-partial saturation bound in fixed-point units
 };
 
 template <int BN, int EPI, int NSTAGE>
@@ -382,6 +390,8 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int et = (warp - 2) * 32 + lane;                   // 0..255
         constexpr int CH = BN / 2;                               // columns per warp
         const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+        unsigned long long glm_q[EPI == EPI2_GLM ? CH / 32 : 1] = {};   // GLM: this lane's column sums over all tiles of the CTA (integers)
+        int glm_nblk = -1;
         int j = 0;
         for (int t = pair; t < total; t += npairs, ++j) {
             const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
@@ -433,6 +443,41 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);   // this accumulator stage may be overwritten
+            } else if (EPI == EPI2_GLM) {
+                const float sy = (row < g.M) ? __ldg(g.gy + row) : 0.f;
+                const bool valid = row < g.M;
+#pragma unroll 1
+                for (int cc = 0; cc < CH / 32; ++cc) {
+                    uint32_t vr[32];
+                    tmem_ld32(taddr + cc * 32, vr);
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float t = __uint_as_float(vr[i]);
+                        float f;
+                        if (g.glm_kind == GLM_LOGISTIC) { const float u = sy * t; f = fmaxf(-u, 0.f) + __logf(1.0f + __expf(-fabsf(u))); }   // softplus(-u) = -log sigmoid(u)
+                        else { const float rr = sy - t; f = rr * rr; }
+                        v[i] = valid ? f : 0.f;
+                    }
+                    // transpose-reduce over the warp's 32 rows: 31 shuffles leave lane L with the sum of column L
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const bool up = (lane & o) != 0;
+                            const float send = up ? v[i] : v[i + o];
+                            const float keep = up ? v[i + o] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    double dq = (double)v[0] * (double)(1 << GLM_FX_SHIFT);
+                    if (!(dq < g.glm_sat)) dq = g.glm_sat;           // hopeless nodes saturate (and read as -inf) instead of wrapping
+                    glm_q[cc] += (unsigned long long)__double2ll_rn(dq);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);
+                glm_nblk = n_blk;
             } else {
                 float z[NCLS];
 #pragma unroll
@@ -485,6 +530,11 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (lane == 0 && q != 0) atomicAdd(g.loss + batch, (unsigned long long)q);
                 }
             }
+        }
+        if (EPI == EPI2_GLM && glm_nblk >= 0) {                  // one global integer add per (lane, column chunk) for the whole CTA
+#pragma unroll
+            for (int cc = 0; cc < (EPI == EPI2_GLM ? CH / 32 : 1); ++cc)
+                if (glm_q[cc]) atomicAdd(g.glm_acc + glm_nblk * BN + chalf * CH + cc * 32 + lane, glm_q[cc]);
         }
     }
     __syncwarp();
@@ -669,6 +719,54 @@ static void free_state(FcState* s) {
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
+
+// ===================================================== GLM heads ==========================================================
+// d-dimensional linear / logistic regression heads on the same GEMM (BASELINE.json calls the simple-net model
+// "Bayesian logistic regression"): t[i][p] = x_i . theta_p for all data rows and ALL P nodes is one [n, d] x [d, P] contraction
+// (bf16x3, fp32 accumulation in TMEM); the epilogue applies softplus(-s_i t) or (y_i - t)^2, reduces over the rows of the tile
+// with warp shuffles and keeps integer per-node sums.
+//   LOGISTIC  loglik_p = sum_i log sigmoid(s_i x_i.theta_p),  s_i = 2 y_i - 1,  theta in R^d
+//   GAUSS     loglik_p = -n/2 log(2 pi sigma_p^2) - sum_i (y_i - x_i.theta_p[0:d])^2 / (2 sigma_p^2),  theta = (coefficients, sigma)
+// theta f32 [P, pitch] -> bf16 [P_pad, 2*Kpad] = [h | l] of the first d coordinates, zero padded
+__global__ void split_theta_kernel(const float* __restrict__ props, int pitch, int d, int P, int P_pad, int Kpad, __nv_bfloat16* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)P_pad * Kpad) return;
+    int r = (int)(i / Kpad), c = (int)(i - (long long)r * Kpad);
+    float v = (r < P && c < d) ? props[(long long)r * pitch + c] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+    __nv_bfloat16* o = out + (long long)r * (2ll * Kpad);
+    o[c] = h; o[Kpad + c] = l;
+}
+__global__ void glm_finalize_kernel(const unsigned long long* __restrict__ acc, const float* __restrict__ props, int pitch, int d, int kind, int P,
+                                    double n_global, double inv_scale, double sat_total, double* __restrict__ lt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double q = (double)(long long)acc[p];
+    const double S = q * (1.0 / (double)(1 << GLM_FX_SHIFT));
+    double v;
+    if (kind == GLM_LOGISTIC) v = -S;
+    else { const double sg = (double)props[(long long)p * pitch + d]; v = -0.5 * n_global * log(6.283185307179586477 * sg * sg) - 0.5 * S / (sg * sg); }
+    v *= inv_scale;
+    if (q >= sat_total || !(v == v)) v = -INFINITY;
+    lt[p] = v;
+}
+
+struct GlmState {
+    long long n_local = 0, n_global = 0;
+    int d = 0, Kpad = 0, P_pad = 0;
+    __nv_bfloat16* xs = nullptr;       // X' [n, 2*Kpad]
+    float* gy = nullptr;               // [n] labels as +1/-1 is built per kind at loglik time from y
+    float* y = nullptr;                // [n] as given
+    int gy_kind = -1;
+    __nv_bfloat16* w = nullptr;        // theta' [P_pad, 2*Kpad]
+    unsigned long long* acc = nullptr; // [P_pad]
+    CUtensorMap tmX, tmW;
+};
+__global__ void glm_signs_kernel(const float* __restrict__ y, float* __restrict__ gy, long long n, int kind) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gy[i] = kind == GLM_LOGISTIC ? (y[i] > 0.5f ? 1.f : -1.f) : y[i];
+}
+
 }  // namespace fc
 }  // namespace pmp
 
@@ -823,6 +921,94 @@ int pmp_large_dim_kernel_term(pmp_ctx* c) {
     fc_dots_kernel<<<dim3(64, P), 256, 0, c->stream>>>(c->d_props, c->d_kt_s1, dim, c->d_kt_dj2, c->d_kt_dot);
     fc_kterm_kernel<<<1, 256, 0, c->stream>>>(c->d_kt_dj2, c->d_kt_dot, P, (double)dim, (double)c->cfg.kernel_sigma, c->d_logw, (c->cfg.flags & PMP_FLAG_KERNEL_MEAN) ? 1 : 0);
     c->launches += 3;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
+int pmp_glm_destroy(pmp_ctx* c) {
+    if (c->glm) {
+        GlmState* s = reinterpret_cast<GlmState*>(c->glm);
+        void* ptrs[] = {s->xs, s->gy, s->y, s->w, s->acc};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        delete s; c->glm = nullptr;
+    }
+    return PMP_OK;
+}
+
+int pmp_set_data_glm(pmp_ctx* c, const float* X, const float* y, int64_t n_local, int64_t n_offset, int64_t n_global, int d) {
+    PMP_REQUIRE(c && X && y && n_local > 0 && n_global >= n_local && d >= 1 && d <= 4096, "bad arguments");
+    PMP_REQUIRE(n_offset % 32 == 0, "GLM shards must start at a multiple of 32 rows (the unit of the order-free integer sums)");
+    PMP_CUDA(cudaSetDevice(c->device));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    pmp_glm_destroy(c);
+    GlmState* s = new GlmState();
+    c->glm = s;
+    s->n_local = n_local; s->n_global = n_global; s->d = d; s->Kpad = (d + BK - 1) / BK * BK;
+    float* d_x32 = nullptr;
+    PMP_CUDA(cudaMalloc((void**)&d_x32, (size_t)n_local * d * sizeof(float)));
+    PMP_CUDA(cudaMalloc((void**)&s->xs, (size_t)n_local * 2 * s->Kpad * sizeof(__nv_bfloat16)));
+    PMP_CUDA(cudaMalloc((void**)&s->y, (size_t)n_local * sizeof(float)));
+    PMP_CUDA(cudaMalloc((void**)&s->gy, (size_t)n_local * sizeof(float)));
+    PMP_CUDA(cudaMemcpyAsync(d_x32, X, (size_t)n_local * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaMemcpyAsync(s->y, y, (size_t)n_local * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    long long tot = n_local * s->Kpad;
+    split2_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_x32, 0, 0, (int)n_local, d, (int)n_local, s->Kpad, s->xs, 1);
+    c->launches++;
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_x32);
+    return make_map(&s->tmX, s->xs, 2 * s->Kpad, n_local, 1, BM);
+}
+
+// fills d_lt[p] for PMP_TARGET_GLM_LOGISTIC / PMP_TARGET_GLM_GAUSS
+int pmp_glm_loglik(pmp_ctx* c) {
+    PMP_REQUIRE(c->glm, "GLM data not set (pmp_set_data_glm)");
+    GlmState* s = reinterpret_cast<GlmState*>(c->glm);
+    const int kind = c->cfg.target == PMP_TARGET_GLM_LOGISTIC ? GLM_LOGISTIC : GLM_GAUSS;
+    const int dim = c->cfg.dim, P = c->P;
+    PMP_REQUIRE(dim == s->d + (kind == GLM_GAUSS ? 1 : 0), "GLM target: dim %d does not match the data (d = %d%s)", dim, s->d, kind == GLM_GAUSS ? " coefficients + sigma" : "");
+    int rc;
+    const int P_pad = (P + 255) / 256 * 256;
+    if (P_pad != s->P_pad) {
+        if (s->w) cudaFree(s->w);
+        if (s->acc) cudaFree(s->acc);
+        s->w = nullptr; s->acc = nullptr; s->P_pad = 0;
+        PMP_CUDA(cudaMalloc((void**)&s->w, (size_t)P_pad * 2 * s->Kpad * sizeof(__nv_bfloat16)));
+        PMP_CUDA(cudaMalloc((void**)&s->acc, (size_t)P_pad * sizeof(unsigned long long)));
+        if ((rc = make_map(&s->tmW, s->w, 2 * s->Kpad, P_pad, 1, 128))) return rc;
+        s->P_pad = P_pad;
+    }
+    if (s->gy_kind != kind) {
+        glm_signs_kernel<<<(unsigned)((s->n_local + 255) / 256), 256, 0, c->stream>>>(s->y, s->gy, s->n_local, kind);
+        c->launches++; s->gy_kind = kind;
+    }
+    long long t = (long long)P_pad * s->Kpad;
+    split_theta_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(c->d_props, dim, s->d, P, P_pad, s->Kpad, s->w);
+    c->launches++;
+    PMP_CUDA(cudaMemsetAsync(s->acc, 0, (size_t)P_pad * sizeof(unsigned long long), c->stream));
+    const int M = (int)s->n_local;
+    const long long parts_global = (s->n_global + 31) / 32 + 8 * 64;          // 32-row partials over all shards (ragged shard tails included)
+    const double sat_total = 4611686018427387904.0, sat = sat_total / (double)parts_global;
+    Gemm2Args g{};
+    g.M = M; g.Kpad = s->Kpad; g.a_shared = 1; g.n_total = P_pad; g.nb = 1; g.a_tiled = 0; g.mb128 = (M + 127) / 128;
+    g.gy = s->gy; g.glm_kind = kind; g.glm_acc = s->acc; g.glm_sat = sat;
+    {
+        constexpr int BN = 256, NSTAGE = 3;
+        constexpr size_t smem = (size_t)NSTAGE * (2 * BM * BK * 2 + 2 * (BN / 2) * BK * 2) + 1024;
+        static bool attr = false;
+        if (!attr) { PMP_CUDA(cudaFuncSetAttribute(fc_gemm2_kernel<BN, EPI2_GLM, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        const int nblk_n = P_pad / BN;
+        const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * nblk_n;
+        long long pairs = (c->sm_count / 2) / nblk_n * nblk_n;                 // a multiple of the node blocks: every pair keeps its node block
+        if (pairs < nblk_n) { set_error("GLM sweep: %d node blocks need at least as many CTA pairs", nblk_n); return PMP_ERR_UNSUPPORTED; }
+        if (pairs > tiles) pairs = (tiles + nblk_n - 1) / nblk_n * nblk_n;
+        fc_gemm2_kernel<BN, EPI2_GLM, NSTAGE><<<dim3((unsigned)(2 * pairs)), GEMM2_THREADS, smem, c->stream>>>(s->tmX, s->tmW, g);
+        c->launches++;
+        PMP_CUDA(cudaGetLastError());
+    }
+    if ((rc = pmp_allreduce_u64(c, s->acc, (size_t)P))) return rc;
+    glm_finalize_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(s->acc, c->d_props, dim, s->d, kind, P, (double)s->n_global, 1.0 / (double)c->cfg.scale, sat_total, c->d_lt);
+    c->launches++;
+    if (c->cfg.algo == PMP_ALGO_MP && !(c->cfg.flags & PMP_FLAG_NO_KERNEL_TERM) && dim > KDIM_MAX) { if ((rc = pmp_large_dim_kernel_term(c))) return rc; }
     PMP_CUDA(cudaGetLastError());
     return PMP_OK;
 }

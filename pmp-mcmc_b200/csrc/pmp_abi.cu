@@ -14,6 +14,8 @@
 #include "chain_persistent_multi.cuh"
 
 extern "C" int pmp_fc_loglik(pmp_ctx* c);   // fc_sweep.cu
+extern "C" int pmp_glm_loglik(pmp_ctx* c);  // fc_sweep.cu
+extern "C" int pmp_glm_destroy(pmp_ctx* c);
 #include "common.cuh"
 #include "sweep_linear.cuh"
 #include "sweep_linear_tc.cuh"
@@ -244,6 +246,7 @@ static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sw
         return PMP_ERR_UNSUPPORTED;
     }
     if (c->cfg.target == PMP_TARGET_FC && (rc = pmp_fc_loglik(c))) return rc;     // GEMM chain + all-reduce of the integer loss sums, all on the ctx stream
+    if ((c->cfg.target == PMP_TARGET_GLM_LOGISTIC || c->cfg.target == PMP_TARGET_GLM_GAUSS) && (rc = pmp_glm_loglik(c))) return rc;
     if ((rc = launch_accept(c, 0, 0, 1, nullptr))) return rc;
     c->host_iter++;
     return PMP_OK;
@@ -371,6 +374,7 @@ int pmp_destroy(pmp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     drop_graph(c);
     pmp_fc_destroy(c);
+    pmp_glm_destroy(c);
     pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     if (c->data_borrowed) { c->d_x = nullptr; c->d_y = nullptr; c->d_bimg = nullptr; }     // owned by another ctx (pmp_share_data)
@@ -410,7 +414,7 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY || cfg->b >= 1, "b=%d must be >= 1", cfg->b);
     PMP_REQUIRE(P >= 1 && P <= MAX_NODES, "P=%lld nodes out of range [1,%d]", P, MAX_NODES);
     PMP_REQUIRE(cfg->dim >= 1, "dim must be >= 1");
-    PMP_REQUIRE(cfg->target >= 0 && cfg->target <= PMP_TARGET_EXTERNAL, "unknown target %d", cfg->target);
+    PMP_REQUIRE(cfg->target >= 0 && cfg->target <= PMP_TARGET_GLM_GAUSS, "unknown target %d", cfg->target);
     PMP_REQUIRE(cfg->algo >= 0 && cfg->algo <= PMP_ALGO_TABLE, "unknown algo %d", cfg->algo);
     PMP_REQUIRE(cfg->draw >= 0 && cfg->draw <= PMP_DRAW_SINGLE, "unknown draw rule %d", cfg->draw);
     if (cfg->target == PMP_TARGET_LINEAR_GAUSS) PMP_REQUIRE(cfg->dim == 3, "linear-Gaussian target has dim 3 (b0,b1,sigma), got %d", cfg->dim);
@@ -419,7 +423,7 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     if (cfg->algo == PMP_ALGO_MH || cfg->algo == PMP_ALGO_BARKER) PMP_REQUIRE(P == 2, "MH/BARKER need P == 2 (FLAT, b=2), got %lld", P);
     if (cfg->algo == PMP_ALGO_PSP) PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY, "PSP needs the BINARY tree");
     if (cfg->algo == PMP_ALGO_PMP) PMP_REQUIRE(cfg->tree == PMP_TREE_BARY || cfg->tree == PMP_TREE_BINARY, "PMP needs a BARY/BINARY tree");
-    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC && cfg->target != PMP_TARGET_EXTERNAL)
+    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC && cfg->target != PMP_TARGET_EXTERNAL && cfg->target != PMP_TARGET_GLM_LOGISTIC && cfg->target != PMP_TARGET_GLM_GAUSS)
         PMP_REQUIRE(cfg->dim <= KDIM_MAX, "in-kernel MP kernel term supports dim <= %d for this target", KDIM_MAX);
     PMP_REQUIRE(cfg->scale != 0.f && cfg->kernel_sigma > 0.f, "scale must be non-zero and kernel_sigma > 0");
 
@@ -574,6 +578,8 @@ int pmp_loglik(pmp_ctx* c, double* out_host) {
         if ((rc = launch_accept(c, 1, 1, 0, nullptr))) return rc;
     } else if (c->cfg.target == PMP_TARGET_FC) {
         if ((rc = pmp_fc_loglik(c))) return rc;
+    } else if (c->cfg.target == PMP_TARGET_GLM_LOGISTIC || c->cfg.target == PMP_TARGET_GLM_GAUSS) {
+        if ((rc = pmp_glm_loglik(c))) return rc;
     } else if (c->cfg.target == PMP_TARGET_EXTERNAL) {
         PMP_REQUIRE(c->lt_valid, "EXTERNAL target: call pmp_write_logtarget first");
     } else {
@@ -797,7 +803,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
         rc = try_run_persistent(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK;
     }
     int64_t done = 0;
-    if (GI > 1 && iters >= GI && c->cfg.target != PMP_TARGET_FC) {     // FC iterations are milliseconds of GEMMs: nothing to gain from a graph
+    if (GI > 1 && iters >= GI && c->cfg.target != PMP_TARGET_FC && c->cfg.target != PMP_TARGET_GLM_LOGISTIC && c->cfg.target != PMP_TARGET_GLM_GAUSS) {     // FC iterations are milliseconds of GEMMs: nothing to gain from a graph
         if (!c->graph_exec || c->graph_iters != GI) {
             drop_graph(c);
             cudaGraph_t graph;
@@ -937,10 +943,11 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks; pa.n_accept = n_accept;
     void* kargs[] = {&pa};
     const void* fn;
+    const int groups = env_int("PMP_MULTI_GROUPS", K >= 4 ? 4 : 2) == 4 ? 4 : 2;       // warp groups per sweep CTA
     switch (c0->cfg.algo) {
-        case PMP_ALGO_MP: fn = (const void*)chain_persistent_multi_kernel<PMP_ALGO_MP>; break;
-        case PMP_ALGO_PSP: fn = (const void*)chain_persistent_multi_kernel<PMP_ALGO_PSP>; break;
-        default: fn = (const void*)chain_persistent_multi_kernel<PMP_ALGO_TABLE>; break;
+        case PMP_ALGO_MP: fn = groups == 4 ? (const void*)chain_persistent_multi_kernel<PMP_ALGO_MP, 4> : (const void*)chain_persistent_multi_kernel<PMP_ALGO_MP, 2>; break;
+        case PMP_ALGO_PSP: fn = groups == 4 ? (const void*)chain_persistent_multi_kernel<PMP_ALGO_PSP, 4> : (const void*)chain_persistent_multi_kernel<PMP_ALGO_PSP, 2>; break;
+        default: fn = groups == 4 ? (const void*)chain_persistent_multi_kernel<PMP_ALGO_TABLE, 4> : (const void*)chain_persistent_multi_kernel<PMP_ALGO_TABLE, 2>; break;
     }
     PMP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
