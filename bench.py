@@ -6,7 +6,7 @@ P = 1024 candidate states per iteration, n = 100 000 data points (BASELINE.json 
 A "step" is one block of ITERS_PER_STEP iterations of every chain, run device-resident.  Between steps L2 is flushed
 (256 MB memset); inside a step the 0.8 MB dataset is re-read from L2 / shared memory by design — that is what a chain does.
 
-Single GPU: the workload is CHAINS (default 4) INDEPENDENT chains of that shape co-scheduled in one cooperative kernel
+Single GPU: the workload is CHAINS (default 8) INDEPENDENT chains of that shape co-scheduled in one cooperative kernel
 (pmp_run_multi): one chain alone is a dependency loop that leaves the sweep SMs idle while it is being accepted, and
 independent repeats are how the reference's experiments are run.  Each chain's trace is bit-identical to the chain run alone
 (tests/test_gpu_multichain.py); `value` counts the proposal evaluations of all chains, `single_chain` in the same JSON line
@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 P_NODES = 1024
 N_DATA = 100000
 ITERS_PER_STEP = 1000
-CHAINS = 4
+CHAINS = 8
 SCALE = 1000.0
 ALPHA = 0.01
 METRIC = "proposal-evals/sec"

@@ -11,6 +11,7 @@
  *                normal()/banana/normal(mu,cov)        simple_sampling/error/error.py:11-14, banana_data.ipynb cell 2,
  *                                                      complex_nets/correlation/com_dim.py:13-21
  *                loss(net) (FC MLP, CE/10)             complex_nets/Mnist/FC/PMP_FC.py:21-44
+ *                d-dimensional logistic / Gaussian     (extension of lb.py:100-108)
  *   propose      host mt19937 generators               500_MP.cu:177-185, 500_PMP.cu:170-179, conv_pmp.cu:182-197,
  *                update()/tree loops                   lb.py:131-136,268-272,354-360
  *   accept       GMOptimizer.step                      lb.py:139-164

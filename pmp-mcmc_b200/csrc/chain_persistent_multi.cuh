@@ -7,7 +7,7 @@
 // chains resident the sweep SMs simply work on chain B while chain A is being accepted:
 //     sweep SMs, warps  0-15 :  | sweep A_i  ....... | wait, nodes | sweep A_i+1 ....... |
 //     sweep SMs, warps 16-31 :  ..... | flush | wait, nodes | sweep B_i ....... | flush |
-//     acceptance CTAs (2)    :  one per chain parity: pre during the sweep, crit when the sums are in, post after the release
+//     acceptance CTAs        :  one per chain: pre during the sweep, crit when the sums are in, post after the release
 // Every chain keeps its own pmp_ctx (state, Philox key, nodes, integer sums, counters, trace ring), executes exactly the
 // arithmetic of chain_persistent_kernel in exactly the same order, and therefore produces bit-identical traces to the same
 // chain run alone (tests/test_gpu_multichain.py).  The data slice of a sweep CTA is staged into shared memory once and is
@@ -99,7 +99,7 @@ struct PersistMultiArgs {
     int n_chains;
     int iters;
     int max_chunks;
-    int n_accept;              // acceptance CTAs: min(K, 2) on one GPU, K when the sums are exchanged with peers
+    int n_accept;              // acceptance CTAs (default: one per chain)
 };
 
 template <int NG>

@@ -792,6 +792,10 @@ static int try_run_persistent_tc(pmp_ctx* c, int64_t iters) {
 // The chain loop.  A CUDA graph of GRAPH_ITERS iterations is captured once per configuration and replayed, so the
 // host issues one launch per GRAPH_ITERS iterations; the iteration counter, the state and the trace cursor live on the
 // device, so replay needs no parameter update.
+static bool peer_fused_ok(pmp_ctx** cs, int K, int64_t iters);
+static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_begin, cudaEvent_t ev_end);
+static thread_local bool g_in_multi_streams = false;    // set while run_multi_streams drives run_impl: that mode is the NCCL path by definition
+
 static int run_impl(pmp_ctx* c, int64_t iters) {
     PMP_REQUIRE(c && c->configured, "ctx not configured");
     PMP_REQUIRE(iters >= 0, "iters < 0");
@@ -799,6 +803,10 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
     const int GI = env_int("PMP_GRAPH_ITERS", 32);
     int rc;
     if (c->cfg.target == PMP_TARGET_LINEAR_GAUSS) {
+        if (c->world > 1 && !g_in_multi_streams) {      // a single sharded chain: the same cooperative kernel, sums exchanged over NVLink peer memory
+            pmp_ctx* one[1] = {c};
+            if (peer_fused_ok(one, 1, iters)) return run_multi_impl(one, 1, iters, nullptr, nullptr);
+        }
         rc = try_run_persistent_tc(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK;
         rc = try_run_persistent(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK;
     }
@@ -871,8 +879,11 @@ static int run_multi_streams(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_
     if (ev_begin) PMP_CUDA(cudaEventRecord(ev_begin, c0->stream));
     PMP_CUDA(cudaEventRecord(c0->ev0, c0->stream));
     for (int k = 1; k < K; ++k) PMP_CUDA(cudaStreamWaitEvent(cs[k]->stream, c0->ev0, 0));
-    int rc;
-    for (int k = 0; k < K; ++k) if ((rc = run_impl(cs[k], iters))) return rc;
+    int rc = PMP_OK;
+    g_in_multi_streams = true;
+    for (int k = 0; k < K && rc == PMP_OK; ++k) rc = run_impl(cs[k], iters);
+    g_in_multi_streams = false;
+    if (rc) return rc;
     for (int k = 1; k < K; ++k) {
         PMP_CUDA(cudaEventRecord(cs[k]->ev1, cs[k]->stream));
         PMP_CUDA(cudaStreamWaitEvent(c0->stream, cs[k]->ev1, 0));
@@ -881,21 +892,35 @@ static int run_multi_streams(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_
     return PMP_OK;
 }
 
+// world_size > 1: can these chains run in the cooperative kernel that exchanges the sums over NVLink peer memory?
+static bool peer_fused_ok(pmp_ctx** cs, int K, int64_t iters) {
+    pmp_ctx* c0 = cs[0];
+    if (!env_int("PMP_PEER_XCHG", 1) || c0->world > PEER_MAX_WORLD || iters < 2 || iters > 2000000000ll || !env_int("PMP_PERSISTENT", 1)) return false;
+    const long long nchunks = (c0->n_local + CHUNK - 1) / CHUNK;
+    const int n_sweep = c0->sm_count - K;
+    if (nchunks == 0 || n_sweep < 1) return false;
+    const long long units = (long long)((c0->P + PERSIST_PT - 1) / PERSIST_PT) * nchunks;
+    const size_t sweep_smem = (size_t)((units + n_sweep - 1) / n_sweep + 1) * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
+    if (sweep_smem > 200 * 1024) return false;
+    for (int k = 0; k < K; ++k) {
+        pmp_ctx* c = cs[k];
+        if (!(c->peers_attached && c->cfg.target == PMP_TARGET_LINEAR_GAUSS && lean_accept_ok(c) && !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) &&
+              c->P == c0->P && c->cfg.algo == c0->cfg.algo && c->d_x == c0->d_x && c->n_local == c0->n_local && c->n_global == c0->n_global)) return false;
+    }
+    return true;
+}
+
 static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
     PMP_REQUIRE(cs && K >= 1 && K <= PERSIST_MAX_CHAINS, "1..%d contexts", PERSIST_MAX_CHAINS);
     PMP_REQUIRE(iters >= 2 && iters <= 2000000000ll, "iters out of range");
     pmp_ctx* c0 = cs[0];
     PMP_REQUIRE(c0 && c0->configured, "ctx 0 not configured");
     if (c0->world > 1) {
-        bool fused = env_int("PMP_PEER_XCHG", 1) != 0 && c0->world <= PEER_MAX_WORLD;
         for (int k = 0; k < K; ++k) {
             PMP_REQUIRE(cs[k] && cs[k]->configured && cs[k]->device == c0->device && cs[k]->world == c0->world && cs[k]->rank == c0->rank, "ctx %d: not configured or another rank / device", k);
             for (int j = 0; j < k; ++j) PMP_REQUIRE(cs[j] != cs[k], "ctx %d given twice", k);
-            pmp_ctx* c = cs[k];
-            fused = fused && c->peers_attached && c->cfg.target == PMP_TARGET_LINEAR_GAUSS && lean_accept_ok(c) && !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) &&
-                    c->P == c0->P && c->cfg.algo == c0->cfg.algo && c->d_x == c0->d_x && c->n_local == c0->n_local && c->n_global == c0->n_global;
         }
-        if (!fused) return run_multi_streams(cs, K, iters, ev_begin, ev_end);
+        if (!peer_fused_ok(cs, K, iters)) return run_multi_streams(cs, K, iters, ev_begin, ev_end);
     }
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
@@ -909,7 +934,11 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
                     "ctx %d does not share ctx 0's data (pmp_share_data)", k);
     }
     PMP_CUDA(cudaSetDevice(c0->device));
-    const int n_accept = c0->world > 1 ? K : (K < 2 ? 1 : 2);      // one acceptance CTA per chain parity; per chain when the sums cross NVLink
+    // Acceptance CTAs, up to one per chain: an acceptance is ~10 us of dependent latencies on one SM, so with fewer acceptance CTAs than chains
+    // the acceptances — not the sweeps — bound the throughput as soon as a sweep is short (measured, n = 12 500, K = 8: 6.2 us per chain
+    // iteration with 2 acceptance CTAs, 2.8 us with 8).  PMP_MULTI_ACCEPT overrides (1..K).
+    int n_accept = c0->world > 1 ? K : (K < 4 ? K : 4);        // one GPU, full dataset: four suffice (10.4 vs 11.0 us per chain iteration at K = 8)
+    { const int ov = env_int("PMP_MULTI_ACCEPT", 0); if (ov >= 1 && ov <= K) n_accept = ov; }
     const int G = c0->sm_count, n_sweep = G - n_accept;
     const long long nchunks = (c0->n_local + CHUNK - 1) / CHUNK;
     PMP_REQUIRE(nchunks > 0 && n_sweep >= 1, "no data");

@@ -256,3 +256,46 @@ class GMpreOptimizerV2(_DeviceSampler):
     def fit(self, data=None, num_steps=1000):
         ctx, tr = self._run(data, num_steps, L.TRACE_SAMPLES)
         return tr["samples"].reshape(num_steps * ctx.P, 3).astype(np.float64)           # lb.py:350,364-368
+
+
+def fit_independent(trainers, data, num_steps=1000):
+    """Independent chains co-scheduled in one cooperative kernel (pmp_run_multi).
+
+    The reference runs its experiments as independent repeats — error.py:191-213 (20 repeats per sampler), lb.py:377-423 (one
+    chain per step size) — one after the other.  Here up to 8 `GMOptimizer` (or up to 8 `preMOptimizer`) trainers with the same
+    N run at once: one chain alone leaves the sweep SMs idle while it is being accepted.  Every trainer keeps its own seed,
+    step size and start state, gets exactly the trace `trainer.fit(data, num_steps)` would return (bit for bit), and ends in
+    the same state.  Returns the list of traces in trainer order."""
+    trainers = list(trainers)
+    if not trainers:
+        return []
+    kind = type(trainers[0])
+    if kind not in (GMOptimizer, preMOptimizer) or any(type(t) is not kind or t.N != trainers[0].N for t in trainers):
+        raise ValueError("fit_independent takes GMOptimizer or preMOptimizer trainers of one kind and one N")
+    what = L.TRACE_SAMPLES if kind is GMOptimizer else L.TRACE_STATE
+    x, y = _to_np(data["x"]).reshape(-1), _to_np(data["y"]).reshape(-1)
+    ctxs = []
+    for k, t in enumerate(trainers):
+        if t._ctx is None or any(t._ctx is c for c in ctxs):
+            t._ctx = _dist.create_context()                    # every chain needs a context of its own
+        ctx = t._ctx
+        ctx.configure(t.tree, b=t._b, depth=t._depth, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=t.algo, draw=t.draw, flags=t.flags,
+                      alpha=float(t.alpha), scale=x.size / 50.0)
+        if k == 0:
+            _dist.set_data_linear_sharded(ctx, x, y)
+        else:
+            ctx.share_data_from(ctxs[0])
+        ctx.set_state(t.net.theta())
+        ctx.seed(t.seed, t._iteration)
+        ctx.trace_config(num_steps, what)
+        ctxs.append(ctx)
+    out = []
+    for lo in range(0, len(ctxs), 8):
+        group = ctxs[lo:lo + 8]
+        L.run_multi(group, num_steps)
+    for t, ctx in zip(trainers, ctxs):
+        tr = ctx.read_trace()
+        t._iteration += num_steps
+        t.net = _net_from_theta(ctx.get_state(), like=t.net)
+        out.append(tr["samples"].reshape(num_steps * ctx.P, 3).astype(np.float64) if kind is GMOptimizer else tr["state"].astype(np.float64))
+    return out

@@ -5,7 +5,7 @@ import numpy as np
 import pmp_mcmc_b200 as pm
 from pmp_mcmc_b200 import _lib as L
 rng = np.random.default_rng(0)
-n, P, iters = 100000, 1024, 2000
+n, P, iters = int(os.environ.get("N", 100000)), 1024, 2000
 x = rng.uniform(-1, 1, n).astype(np.float32); y = (-1 + 2 * x + 0.5 * rng.standard_normal(n)).astype(np.float32)
 out = {}
 for K in (1, 2, 4, 6, 8):

@@ -102,6 +102,24 @@ def main():
     os.environ["PMP_PEER_XCHG"] = "1"
     L.run_multi([ctx, ctx2], a.iters)                       # a second fused launch continues the exchange counters
     assert ctx.iteration() == 2 * a.iters and ctx2.iteration() == 2 * a.iters
+    # FC and GLM sweeps on sharded rows: integer loss sums all-reduced inside the library → the same bits as one GPU
+    from oracle import oracle as o
+    rng = np.random.default_rng(31)
+    nf = 1500
+    Xf = rng.standard_normal((nf, 784)).astype(np.float32); yf = rng.integers(0, 10, size=nf).astype(np.int64)
+    ctx.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-3, scale=10.0)
+    lo, hi = pdist.shard_bounds(nf, world, rank, align=128)
+    ctx.set_data_fc(Xf[lo:hi], yf[lo:hi], n_offset=lo, n_global=nf)
+    ctx.set_state(o.fc_init_theta(2)); ctx.seed(21, 0); ctx.propose()
+    res["fc_lt"] = ctx.loglik()
+    ng, dg = 5000, 20
+    Xg = rng.standard_normal((ng, dg)).astype(np.float32); yg = (rng.uniform(size=ng) < 0.5).astype(np.float32)
+    thg = (0.3 * rng.standard_normal((50, dg))).astype(np.float32)
+    ctx.configure(L.TREE_FLAT, b=50, dim=dg, target=L.TARGET_GLM_LOGISTIC, algo=L.ALGO_TABLE, draw=L.DRAW_SINGLE, flags=L.FLAG_NO_KERNEL_TERM, alpha=0.0, scale=100.0)
+    lo, hi = pdist.shard_bounds(ng, world, rank)
+    ctx.set_data_glm(Xg[lo:hi], yg[lo:hi], n_offset=lo, n_global=ng)
+    ctx.write_proposals(thg)
+    res["glm_lt"] = ctx.loglik()
     if rank == 0:
         np.savez(a.out, world=world, **res)
     ctx2.close()

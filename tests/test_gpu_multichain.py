@@ -79,3 +79,18 @@ def test_run_multi_rejects_unshared_data():
     with pytest.raises(L.PmpError, match="share"):
         L.run_multi([a, b], 10)
     b.close(); a.close()
+
+
+def test_fit_independent_equals_fit():
+    """samplers.fit_independent: lb.py trainers co-scheduled; each gets the trace its own fit() returns."""
+    from pmp_mcmc_b200 import samplers as S
+    x, y = synthetic_linear(4000, seed=8)
+    data = {"x": x, "y": y}
+    solo = []
+    for k, alpha in enumerate((0.01, 0.03, 0.1)):
+        t = S.GMOptimizer(S.BayesNet(), alpha, N=7, seed=40 + k)
+        solo.append((t.fit(data, 30), t.net.theta()))
+    trainers = [S.GMOptimizer(S.BayesNet(), alpha, N=7, seed=40 + k) for k, alpha in enumerate((0.01, 0.03, 0.1))]
+    traces = S.fit_independent(trainers, data, 30)
+    for (ref, th), tr, t in zip(solo, traces, trainers):
+        assert tr.shape == (30 * 8, 3) and np.array_equal(tr, ref) and np.array_equal(t.net.theta(), th)

@@ -69,5 +69,19 @@ def test_sharded_chain_equals_single_gpu_chain(tmp_path):
             tr = c.read_trace()
             for k in ("state", "next", "draws", "logw"):
                 assert np.array_equal(tr[k], g[tag + "_" + k]), (tag, k)
+        # FC and GLM sweeps: sharded rows + all-reduced integer sums give the single-GPU bits
+        from oracle import oracle as o
+        rng = np.random.default_rng(31)
+        nf = 1500
+        Xf = rng.standard_normal((nf, 784)).astype(np.float32); yf = rng.integers(0, 10, size=nf).astype(np.int64)
+        c.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-3, scale=10.0)
+        c.set_data_fc(Xf, yf); c.set_state(o.fc_init_theta(2)); c.seed(21, 0); c.propose()
+        assert np.array_equal(c.loglik(), g["fc_lt"])
+        ng, dg = 5000, 20
+        Xg = rng.standard_normal((ng, dg)).astype(np.float32); yg = (rng.uniform(size=ng) < 0.5).astype(np.float32)
+        thg = (0.3 * rng.standard_normal((50, dg))).astype(np.float32)
+        c.configure(L.TREE_FLAT, b=50, dim=dg, target=L.TARGET_GLM_LOGISTIC, algo=L.ALGO_TABLE, draw=L.DRAW_SINGLE, flags=L.FLAG_NO_KERNEL_TERM, alpha=0.0, scale=100.0)
+        c.set_data_glm(Xg, yg); c.write_proposals(thg)
+        assert np.array_equal(c.loglik(), g["glm_lt"])
     finally:
         c.close()
