@@ -160,3 +160,20 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle mirror", "").replace("the oracle", "").replace("oracle_blocked_cdf", "").replace("oracle/", "").replace("oracle.", "") or f.endswith((".cu", ".cuh")), f
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_glm_oracle_against_scipy():
+    """oracle.loglik_glm_f64 (checker of the d-dimensional heads): logistic vs scipy's expit / log, Gaussian vs scipy.stats.norm."""
+    from scipy import stats
+    from scipy.special import expit
+    from oracle import oracle as o
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((400, 7)); yb = (rng.uniform(size=400) < 0.4).astype(float); yr = rng.standard_normal(400)
+    th = rng.standard_normal((5, 7)) * 0.5
+    ll = o.loglik_glm_f64(X, yb, th, "logistic", scale=8.0)
+    ref = np.array([np.sum(np.where(yb > 0.5, np.log(expit(X @ t)), np.log(expit(-(X @ t))))) for t in th]) / 8.0
+    np.testing.assert_allclose(ll, ref, rtol=1e-12)
+    thg = np.concatenate([th, rng.uniform(0.5, 2, (5, 1))], axis=1)
+    lg = o.loglik_glm_f64(X, yr, thg, "gauss", scale=8.0)
+    refg = np.array([stats.norm(X @ t[:-1], t[-1]).logpdf(yr).sum() for t in thg]) / 8.0
+    np.testing.assert_allclose(lg, refg, rtol=1e-12)
