@@ -41,6 +41,12 @@ def main():
             def set_data_linear(self, xs, ys, n_offset=0, n_global=None):
                 made.update(lo=n_offset, n_local=len(xs), n_global=n_global, sx=float(np.sum(xs, dtype=np.float64)))
 
+            def peer_exchange_handle(self):          # a stand-in IPC handle that names its rank
+                return bytes([self.rank]) * 64
+
+            def peer_exchange_attach(self, handles):
+                made.update(handles=bytes(handles))
+
         real = L.Context
         L.Context = FakeContext
         try:
@@ -49,6 +55,8 @@ def main():
         finally:
             L.Context = real
         assert made["uid"] == bytes(range(128)) and made["world_size"] == world and made["rank"] == rank
+        # dist.attach_peers: every rank receives all exchange-buffer handles, rank-major (what pmp_peer_exchange_attach expects)
+        assert made["handles"] == b"".join(bytes([r]) * 64 for r in range(world))
         assert lo % 64 == 0 and made["n_global"] == a.n and made["n_local"] == hi - lo
         t = torch.tensor([float(hi - lo), made["sx"]], dtype=torch.float64)
         td.all_reduce(t)
