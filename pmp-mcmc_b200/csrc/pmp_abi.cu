@@ -972,12 +972,15 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks; pa.n_accept = n_accept;
     void* kargs[] = {&pa};
     const void* fn;
-    const int groups = env_int("PMP_MULTI_GROUPS", K >= 4 ? 4 : 2) == 4 ? 4 : 2;       // warp groups per sweep CTA
+    int groups = env_int("PMP_MULTI_GROUPS", K >= 4 ? 4 : 2);                          // warp groups per sweep CTA
+    if (groups != 2 && groups != 4 && groups != 8) groups = K >= 4 ? 4 : 2;
+#define PMP_MULTI_FN(ALGO) (groups == 8 ? (const void*)chain_persistent_multi_kernel<ALGO, 8> : groups == 4 ? (const void*)chain_persistent_multi_kernel<ALGO, 4> : (const void*)chain_persistent_multi_kernel<ALGO, 2>)
     switch (c0->cfg.algo) {
-        case PMP_ALGO_MP: fn = groups == 4 ? (const void*)chain_persistent_multi_kernel<PMP_ALGO_MP, 4> : (const void*)chain_persistent_multi_kernel<PMP_ALGO_MP, 2>; break;
-        case PMP_ALGO_PSP: fn = groups == 4 ? (const void*)chain_persistent_multi_kernel<PMP_ALGO_PSP, 4> : (const void*)chain_persistent_multi_kernel<PMP_ALGO_PSP, 2>; break;
-        default: fn = groups == 4 ? (const void*)chain_persistent_multi_kernel<PMP_ALGO_TABLE, 4> : (const void*)chain_persistent_multi_kernel<PMP_ALGO_TABLE, 2>; break;
+        case PMP_ALGO_MP: fn = PMP_MULTI_FN(PMP_ALGO_MP); break;
+        case PMP_ALGO_PSP: fn = PMP_MULTI_FN(PMP_ALGO_PSP); break;
+        default: fn = PMP_MULTI_FN(PMP_ALGO_TABLE); break;
     }
+#undef PMP_MULTI_FN
     PMP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, smem));

@@ -8,7 +8,7 @@ rng = np.random.default_rng(0)
 n, P, iters = int(os.environ.get("N", 100000)), 1024, 2000
 x = rng.uniform(-1, 1, n).astype(np.float32); y = (-1 + 2 * x + 0.5 * rng.standard_normal(n)).astype(np.float32)
 out = {}
-for K in (1, 2, 4, 6, 8):
+for K in [int(k) for k in os.environ.get("KS", "1,2,4,6,8").split(",")]:
     ctxs = []
     for i in range(K):
         c = pm.Context(0)
