@@ -44,9 +44,9 @@ UNIT = "proposal-evals/s"
 BASELINE_EVALS_PER_S = 1024 / ((33473.53 + 1099.258) * 1e-6)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full: the dataset is read from HBM once per launch and
 # then lives in shared memory.  Single chain: profiles/r1b_chain_persistent_ncu_full_summary.txt (50-iteration launch);
-# co-scheduled chains: profiles/r1c_chain_persistent_multi_ncu_full_summary.txt (4 chains x 1000 iterations: the launch the bench times).
+# co-scheduled chains: profiles/r1c_chain_persistent_multi_ncu_full_summary.txt (8 chains x 1000 iterations: the launch the bench times).
 NCU_DRAM_BYTES_PER_LAUNCH = 914944 + 2304
-NCU_DRAM_BYTES_PER_LAUNCH_MULTI = 1004288 + 58112
+NCU_DRAM_BYTES_PER_LAUNCH_MULTI = 1131008 + 101376
 
 
 def synthetic(n, seed=0):
