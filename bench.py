@@ -3,23 +3,28 @@
 P = 1024 candidate states per iteration, n = 100 000 data points (BASELINE.json metric; the reference's
 `100000_MP.cu` time-analysis shape: flat proposals, CUDA draw rule, SCALE 1000, alpha 0.01, theta0 = (1,1,1)).
 
-A "step" is one block of ITERS_PER_STEP iterations of every chain, run device-resident.  Between steps L2 is flushed
-(256 MB memset); inside a step the 0.8 MB dataset is re-read from L2 / shared memory by design — that is what a chain does.
+`value` is ONE chain — the reference's shape (README.md:39-48 times one chain; BASELINE config 3 is one chain, sharded) — run
+device-resident: a "step" is one block of ITERS_PER_STEP iterations.  Between steps L2 is flushed (256 MB memset); inside a step the
+0.8 MB dataset is re-read from L2 / shared memory by design — that is what a chain does.  `vs_baseline` and `roofline` are this chain's.
 
-Single GPU: the workload is CHAINS (default 8) INDEPENDENT chains of that shape co-scheduled in one cooperative kernel
-(pmp_run_multi): one chain alone is a dependency loop that leaves the sweep SMs idle while it is being accepted, and
-independent repeats are how the reference's experiments are run.  Each chain's trace is bit-identical to the chain run alone
-(tests/test_gpu_multichain.py); `value` counts the proposal evaluations of all chains, `single_chain` in the same JSON line
-is one chain alone (pmp_run), so both the throughput and the latency-bound figure are on record.
+Everything else the path offers is reported under its own key, each with its own roofline block, never mixed into `value`:
+    co_scheduled     K independent chains of the same shape in one cooperative kernel (pmp_run_multi): the throughput figure —
+                     a single chain is a dependency loop that leaves the sweep SMs idle while it is being accepted
+    pmp_binary_d10   the `100000_PMP.cu` shape (binary prefetch tree D = 10, table rule as shipped)
+    n500             the n = 500 rows of the reference's table (P = 4 and 1024): iterations/s against an empty-iteration latency floor
+    analytic         batched banana / normal chains: GB/s against the HBM peak
+    fc               BASELINE config 5: FC 784-512-256-128-10, n = 60 000, P = 1024 (binary tree D = 10), rows sharded over the ranks
+    parity           sha256 of chain 0's (accepted index, state) trace at this --gpus N == the same chain run alone on one GPU (asserted)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1 is launched by torchrun (one rank per GPU); the dataset is sharded (strong scaling: n stays 100 000, as BASELINE
-config 3 names it) and the per-node partial sums are all-reduced with NCCL inside the library.
-`--impl reference` times the reference's CPU implementation of the same path (oracle port of lb.py's per-proposal
-torch loop; /root/reference cannot travel to the GPU box) on the host cores.
+N > 1 is launched by torchrun (one rank per GPU); the dataset is sharded (strong scaling: n stays 100 000, as BASELINE config 3 names
+it) and the per-node partial sums are exchanged inside the chain kernel over NVLink peer memory (NCCL when PMP_PEER_XCHG=0).
+`--impl reference` times the reference's OWN CPU implementation of the path — simple_net/lb.py, staged unmodified into oracle/_ref/pysrc by
+`make -C oracle` (the oracle port when that is absent) — on the host cores, all threads.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,18 +40,15 @@ sys.path.insert(0, ROOT)
 P_NODES = 1024
 N_DATA = 100000
 ITERS_PER_STEP = 1000
-CHAINS = 8
+CHAINS = 16
 SCALE = 1000.0
 ALPHA = 0.01
 METRIC = "proposal-evals/sec"
 UNIT = "proposal-evals/s"
-# README.md:44 of the reference (V100): MP, n=100000, P=1024: 33473.53 us kernel + 1099.258 us host/copy per iteration
+# README.md:44 of the reference: MP, n=100000, P=1024: 33473.53 us kernel + 1099.258 us host/copy per iteration.  The README says "Tesla A100"
+# (README.md:20); the shipped .nvvp profiler databases identify the device as a Tesla V100-SXM2-32GB.
 BASELINE_EVALS_PER_S = 1024 / ((33473.53 + 1099.258) * 1e-6)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full: the dataset is read from HBM once per launch and
-# then lives in shared memory.  Single chain: profiles/r1b_chain_persistent_ncu_full_summary.txt (50-iteration launch);
-# co-scheduled chains: profiles/r1c_chain_persistent_multi_ncu_full_summary.txt (8 chains x 1000 iterations: the launch the bench times).
-NCU_DRAM_BYTES_PER_LAUNCH = 914944 + 2304
-NCU_DRAM_BYTES_PER_LAUNCH_MULTI = 1131008 + 101376
+FC_N, FC_DEPTH, FC_DIM = 60000, 10, 567434
 
 
 def synthetic(n, seed=0):
@@ -54,6 +56,13 @@ def synthetic(n, seed=0):
     x = rng.uniform(-1, 1, n).astype(np.float32)
     y = (-1.0 + 2.0 * x + 0.5 * rng.standard_normal(n)).astype(np.float32)
     return x, y
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -87,17 +96,84 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_evals_per_s(x, y, n_evals, threads=None):
-    """The reference's CPU path for one sweep: a Python loop of BayesNet.loglik (lb.py:103-108, torch float32)."""
-    from oracle import oracle
+# ---------------------------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own implementation of the path (checker / baseline only — never on the product path)
+def host_threads():
+    """All host cores: torchrun exports OMP_NUM_THREADS=1, which would pin the reference arm to one core."""
     import torch
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def reference_lb():
+    """simple_net/lb.py definitions (lines 1-376) — the mounted tree here, the staged unmodified copy on the GPU box; None when neither exists."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.python_available():
+            return ref_loader.load_lb()
+    except Exception:
+        pass
+    return None
+
+
+def make_lb_nets(lb, thetas):
+    import torch
+    nets = {}
+    for i, th in enumerate(thetas):
+        net = lb["BayesNet"]()
+        with torch.no_grad():
+            net.beta0.copy_(torch.tensor([float(th[0])])); net.beta.copy_(torch.tensor([float(th[1])])); net.sigma.copy_(torch.tensor([float(th[2])]))
+        nets[i] = net
+    return nets
+
+
+def cpu_sweep_evals_per_s(x, y, n_evals):
+    """The reference's CPU path for one sweep: the Python loop `[net.loglik(data) for net in proposal_nets]` of GMOptimizer.step (lb.py:150,
+    BayesNet.loglik lb.py:103-108).  Returns (evals/s, cores, seconds, kind)."""
+    import torch
+    cores = host_threads()
     rng = np.random.default_rng(1)
-    nets = (np.array([1, 1, 1], np.float32) + ALPHA * rng.standard_normal((n_evals, 3))).astype(np.float32)
-    oracle.loglik_lb_torch(x, y, nets[:8], threads)      # warm-up
+    thetas = (np.array([1, 1, 1], np.float32) + ALPHA * rng.standard_normal((n_evals, 3))).astype(np.float32)
+    lb = reference_lb()
+    if lb is not None:
+        data = {"x": torch.from_numpy(x), "y": torch.from_numpy(y)}
+        nets = make_lb_nets(lb, thetas)
+        for i in range(min(8, n_evals)):
+            nets[i].loglik(data)
+        t0 = time.perf_counter()
+        for i in range(n_evals):                                   # lb.py:150 verbatim: `proposal_nets[i].loglik(data).item()` (autograd enabled, as in the reference)
+            nets[i].loglik(data).item()
+        dt = time.perf_counter() - t0
+        return n_evals / dt, cores, dt, "reference"
+    from oracle import oracle
+    oracle.loglik_lb_torch(x, y, thetas[:8], cores)
     t0 = time.perf_counter()
-    oracle.loglik_lb_torch(x, y, nets, threads)
+    oracle.loglik_lb_torch(x, y, thetas, cores)
     dt = time.perf_counter() - t0
-    return n_evals / dt, torch.get_num_threads(), dt
+    return n_evals / dt, cores, dt, "port"
+
+
+def cpu_full_step(x, y, P):
+    """One full GMOptimizer.step of the reference (lb.py:139-164: the sweep AND the (N+1)^2 log_trans_prob calls, pandas draw) at a P the
+    CPU finishes in seconds.  None without the reference's Python."""
+    import torch
+    lb = reference_lb()
+    if lb is None:
+        return None
+    host_threads()
+    rng = np.random.default_rng(2)
+    thetas = (np.array([1, 1, 1], np.float32) + ALPHA * rng.standard_normal((P, 3))).astype(np.float32)
+    thetas[:, 2] = np.abs(thetas[:, 2])
+    data = {"x": torch.from_numpy(x), "y": torch.from_numpy(y)}
+    nets = make_lb_nets(lb, thetas)
+    opt = lb["GMOptimizer"](nets[0], ALPHA, N=P - 1)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    opt.step(data, nets)
+    dt = time.perf_counter() - t0
+    return {"P": P, "seconds_per_step": dt, "value": P / dt, "unit": UNIT,
+            "what": "GMOptimizer.step (lb.py:139-164) at n=%d: %d loglik passes + %d log_trans_prob calls + pandas draw" % (len(x), P, P * (P - 1))}
 
 
 def reference_cuda_kernel(x, y, P):
@@ -130,20 +206,141 @@ def run_reference(args):
     x, y = synthetic(N_DATA)
     evals = 256          # bounded sample of the 1024-proposal sweep per step
     vals = []
+    kind, cores = "port", 1
     for s in range(args.warmup + args.steps):
-        v, cores, dt = cpu_port_evals_per_s(x, y, evals)
+        v, cores, dt, kind = cpu_sweep_evals_per_s(x, y, evals)
         if s >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3 * (P_NODES / evals)
+    src = "the reference's own simple_net/lb.py (BayesNet.loglik, lb.py:103-108), unmodified" if kind == "reference" else "oracle port of lb.py:103-108 (oracle.loglik_lb_torch)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32",
             "data": "synthetic", "iters_per_sec": value / P_NODES,
-            "config": {"workload": "simple_net linear-Gaussian MP, P=1024, n=100000 (lb.py BayesNet.loglik per proposal on the host)", "P": P_NODES, "n": N_DATA},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d of the 1024 proposal-evaluations per step at n=100000, torch CPU float32 loop (oracle.loglik_lb_torch)" % evals},
+            "config": {"workload": "simple_net linear-Gaussian MP, P=1024, n=100000: the bare sweep `[net.loglik(data) for net in proposal_nets]` on the host (no log_trans_prob, no draw — generous to the reference)", "P": P_NODES, "n": N_DATA},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d of the 1024 proposal-evaluations per step at n=100000, torch CPU float32, %s" % (evals, src)},
+            "full_step": cpu_full_step(x, y, 32),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+def trace_digest(tr):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(tr["next"], dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(tr["state"], dtype=np.float32).tobytes())
+    return h.hexdigest()
+
+
+def extra_n500(pm, L, dev, peak):
+    """The n = 500 rows of the reference's table (README.md:41-42,45-46): P = 4 and P = 1024, MP, SCALE 10.  Work per iteration is 12 kflop /
+    3 Mflop: iterations/s is set by the per-iteration hand-offs, so it is reported against an EMPTY-iteration floor (n = 64, P = 4: one chunk)."""
+    out = {}
+    c = pm.Context(dev)
+    try:
+        def its(n, P, iters=4000):
+            x, y = synthetic(n, seed=5)
+            c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=ALPHA, scale=10.0)
+            c.set_data_linear(x, y); c.set_state([1, 1, 1]); c.seed(7, 0)
+            c.run(200)
+            ms = min(c.run_timed(iters)[0] for _ in range(3))
+            return iters / (ms * 1e-3)
+        floor = its(64, 4)
+        ref = {4: 1e6 / (157.505 + 115.84), 1024: 1e6 / (452.258 + 1066.212)}
+        for P in (4, 1024):
+            v = its(500, P)
+            out["P%d" % P] = {"iters_per_sec": v, "us_per_iter": 1e6 / v, "proposal_evals_per_s": v * P, "vs_baseline": v / ref[P],
+                              "roofline": {"bound": "latency", "achieved": v, "peak": floor, "unit": "it/s", "frac": v / floor,
+                                           "fp32_tflops": 6.0 * 500 * P * v / 1e12, "fp32_frac": 6.0 * 500 * P * v / 1e12 / peak,
+                                           "note": "an iteration is two L2 hand-offs + one acceptance on one SM; peak = the same loop on one 64-point chunk, P = 4"}}
+        out["empty_iteration_floor_iters_per_sec"] = floor
+        out["baseline"] = "reference README.md:41-42 (V100): MP n=500 P=4 157.505+115.84 us, P=1024 452.258+1066.212 us per iteration"
+    finally:
+        c.close()
+    return out
+
+
+def extra_pmp_binary(pm, L, dev, x, y, peak, iters):
+    """The `100000_PMP.cu` shape (README.md:48): binary prefetch tree D = 10 (P = 1024), table rule as shipped, CUDA draw rule, SCALE 1000."""
+    c = pm.Context(dev)
+    try:
+        c.configure(L.TREE_BINARY, depth=10, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_TABLE, draw=L.DRAW_CUDA, alpha=ALPHA, scale=SCALE,
+                    flags=L.FLAG_QUIRK_TABLE_CONST)
+        c.set_data_linear(x, y); c.set_state([1, 1, 1]); c.seed(11, 0)
+        c.run(200)
+        ms = min(c.run_timed(iters)[0] for _ in range(3))
+        v = iters / (ms * 1e-3)
+        tf = 6.0 * len(x) * P_NODES * v / 1e12
+        return {"iters_per_sec": v, "us_per_iter": 1e6 / v, "value": v * P_NODES, "unit": UNIT, "vs_baseline": v / (1e6 / (42096.793 + 2041.279)),
+                "baseline": "reference README.md:48 (V100): PMP n=100000 P=1024 42096.793+2041.279 us per iteration",
+                "roofline": {"bound": "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "kernel": "chain_persistent_kernel<TABLE> (one launch per step)"}}
+    finally:
+        c.close()
+
+
+def extra_analytic(pm, L, dev, hbm):
+    """Batched independent chains on the banana target (BASELINE config 1 shape: N+1 = 4, D = 2 -> 16 nodes), samples recorded."""
+    c = pm.Context(dev)
+    try:
+        out = {}
+        for name, cfg, chains, iters in (
+                ("banana_pmp_16", dict(tree=L.TREE_BARY, b=4, depth=2, dim=2, target=L.TARGET_BANANA, algo=L.ALGO_PMP, draw=L.DRAW_PYTHON, alpha=1.0, flags=L.FLAG_QUIRK_LEVEL_MOD), 1 << 20, 24),
+                ("stdnormal40_psp_8", dict(tree=L.TREE_BINARY, b=2, depth=3, dim=40, target=L.TARGET_STDNORMAL, algo=L.ALGO_PSP, draw=L.DRAW_PYTHON, alpha=0.5, kernel_sigma=0.5), 1 << 17, 24)):
+            c.configure(**cfg); c.seed(0, 0)
+            c.chains_create(chains)
+            c.chains_run_timed(2, True)
+            ms = min(c.chains_run_timed(iters, True) for _ in range(3))
+            evals = float(chains) * iters * c.P
+            gbs = evals * cfg["dim"] * 4 / (ms * 1e-3) / 1e9
+            out[name] = {"chains": chains, "iters": iters, "ms": ms, "node_evals_per_s": evals / (ms * 1e-3), "chain_iters_per_s": chains * iters / (ms * 1e-3),
+                         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                      "what": "algorithmic bytes = 4*dim per node evaluation (the recorded resampled points, SURVEY 8d)"}}
+        return out
+    finally:
+        c.close()
+
+
+def extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps):
+    """BASELINE config 5: FC 784-512-256-128-10 on synthetic MNIST-shaped rows, n = 60 000 sharded over the ranks, P = 1024 nodes (binary
+    prefetch tree D = 10, PMP_FC.py:105-143 rule), theta0 = the reference's FC_model.pkl (tests/golden/fc_theta0.npy).  One iteration =
+    propose 1023 x 567 434 increments, the P forward passes as tcgen05 GEMM chains, all-reduce of the P integer loss sums, acceptance."""
+    n = FC_N
+    rng = np.random.default_rng(0)
+    lo, hi = pdist.shard_bounds(n, world, rank, align=128)
+    X = rng.standard_normal((n, 784), dtype=np.float32)
+    yl = rng.integers(0, 10, size=n).astype(np.int64)
+    try:
+        theta0 = np.load(os.path.join(ROOT, "tests", "golden", "fc_theta0.npy"))
+        theta_src = "FC_model.pkl"
+    except OSError:
+        theta0 = (rng.uniform(-1, 1, FC_DIM) * 0.04).astype(np.float32)
+        theta_src = "random init"
+    ctx.configure(L.TREE_BINARY, depth=FC_DEPTH, dim=FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+    ctx.set_data_fc(X[lo:hi], yl[lo:hi], n_offset=lo, n_global=n)
+    del X
+    ctx.set_state(theta0); ctx.seed(1, 0)
+    ctx.trace_config(2 + steps, L.TRACE_NEXT)
+    ctx.run(1)                                                   # warm-up iteration
+    ms = []
+    for _ in range(steps):
+        ms.append(max_over_ranks(ctx.run_timed(1)[0]))
+    nxt = ctx.read_trace()["next"]
+    ctx.propose(); ctx.sync()
+    t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = max_over_ranks(time.perf_counter() - t0)
+    lt = ctx.loglik()
+    P = 1 << FC_DEPTH
+    it_s = float(np.mean(ms)) * 1e-3
+    alg = 2.0 * 566528 * n * P
+    peak = peaks.get("bf16_tflops_sustained", 1383.9) * world
+    mode = os.environ.get("PMP_FC_MODE", "delta")
+    return {"workload": "FC 784-512-256-128-10, n=%d rows sharded over %d rank(s), P=%d nodes (binary tree D=%d), alpha=1e-4, theta0=%s" % (n, world, P, FC_DEPTH, theta_src),
+            "value": P / it_s, "unit": UNIT, "iters_per_sec": 1.0 / it_s, "ms_per_iter": it_s * 1e3, "sweep_ms": sweep_s * 1e3, "accepted": [int(v) for v in nxt],
+            "logtarget_range": [float(lt.min()), float(lt.max())], "contraction": mode,
+            "roofline": {"bound": "tensor", "achieved": alg / sweep_s / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": alg / sweep_s / 1e12 / peak,
+                         "achieved_whole_iteration": alg / it_s / 1e12, "frac_whole_iteration": alg / it_s / 1e12 / peak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus" if peaks else "fallback 1383.9 x n_gpus",
+                         "note": "ALGORITHMIC flops 2*566528*n per node; `achieved` times the P-node sweep (pmp_loglik) alone, `achieved_whole_iteration` one full pmp_run iteration (propose + sweep + all-reduce + acceptance)"}}
 
 
 def main():
@@ -154,10 +351,12 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--iters-per-step", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--weak", action="store_true", help="n = 100000 per GPU instead of 100000 in total")
-    ap.add_argument("--chains", type=int, default=CHAINS, help="independent chains co-scheduled on one GPU (1: a single chain with pmp_run)")
+    ap.add_argument("--chains", type=int, default=CHAINS, help="independent chains of the co_scheduled block (pmp_run_multi)")
+    ap.add_argument("--skip", default="", help="comma list of extra blocks to skip: co,n500,pmp,analytic,fc,cpu")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    skip = set(filter(None, args.skip.split(",")))
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     import torch
@@ -173,47 +372,20 @@ def main():
     n_global = N_DATA * world if args.weak else N_DATA
     x, y = synthetic(n_global)
     xp, yp = torch.from_numpy(x).pin_memory().numpy(), torch.from_numpy(y).pin_memory().numpy()     # pinned host buffers for the e2e arm
-
-    # N = 1: the chains share one cooperative kernel.  N > 1: every chain's data are sharded over the ranks; the same kernel runs on
-    # every GPU and exchanges the per-node integer sums through NVLink peer memory (pmp_peer_exchange_*, attached by
-    # dist.create_context); PMP_PEER_XCHG=0 falls back to one stream + NCCL communicator per chain.
-    chains = max(1, min(8, args.chains))
+    peaks = load_peaks()
+    WHAT = L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS
 
     def configure(c):
         c.configure(L.TREE_FLAT, b=P_NODES, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=ALPHA, scale=SCALE)
 
     configure(ctx)
     lo, hi = pdist.set_data_linear_sharded(ctx, xp, yp)
-    ctxs = [ctx]
-    for k in range(1, chains):
-        c = pdist.create_context(local)
-        configure(c)
-        c.share_data_from(ctx)
-        ctxs.append(c)
 
-    def reset(seed0):
-        for k, c in enumerate(ctxs):
-            c.set_state([1, 1, 1]); c.seed(seed0 + k, 0)
-
-    def run_step(timed):
-        if chains == 1:
-            if timed:
-                return ctx.run_timed(iters)[0]
-            ctx.run(iters)
-            return None
-        if timed:
-            return L.run_multi_timed(ctxs, iters)
-        L.run_multi(ctxs, iters)
-        return None
-
-    reset(2024)
-    fused_multi = world > 1 and chains > 1 and all(c.peers_attached for c in ctxs) and os.environ.get("PMP_PEER_XCHG", "1") != "0"
-
-    def barrier():
+    def barrier(cs=(ctx,)):
         if world > 1:
             td.barrier()
         torch.cuda.synchronize()
-        for c in ctxs:
+        for c in cs:
             c.sync()
 
     def max_over_ranks(v):
@@ -223,128 +395,173 @@ def main():
         td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident arm: inputs already in HBM, CUDA events on the ctx stream, max over ranks -------------------
+    # ---- ONE chain, device-resident: inputs already in HBM, CUDA events on the ctx stream, max over ranks (`value`) ------------
+    ctx.set_state([1, 1, 1]); ctx.seed(2024, 0)
     for _ in range(args.warmup):
-        ctx.l2_flush(); run_step(False)
+        ctx.l2_flush(); ctx.run(iters)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = sum(c.launch_count() for c in ctxs)
+    launches0 = ctx.launch_count()
     step_ms = []
     for _ in range(args.steps):
         ctx.l2_flush()
         barrier()
-        step_ms.append(max_over_ranks(run_step(True)))
+        step_ms.append(max_over_ranks(ctx.run_timed(iters)[0]))
     barrier()
-    launches = sum(c.launch_count() for c in ctxs) - launches0
-    total_s = sum(step_ms) * 1e-3
+    launches = ctx.launch_count() - launches0
     clocks = sampler.summary()
-    iters_per_s = args.steps * iters * chains / total_s            # chain iterations per second, all chains
+    total_s = sum(step_ms) * 1e-3
+    iters_per_s = args.steps * iters / total_s
     value = iters_per_s * P_NODES
 
-    # ---- one chain alone (pmp_run): the latency-bound figure -------------------------------------------------------------
-    single = None
-    if chains > 1:
-        ctx.set_state([1, 1, 1]); ctx.seed(2024, 0)
-        ctx.l2_flush(); ctx.run(iters)
-        ms1 = []
-        for _ in range(3):
-            ctx.l2_flush(); ctx.sync()
-            ms1.append(ctx.run_timed(iters)[0])
-        us1 = float(np.mean(ms1)) * 1e3 / iters
-        single = {"value": P_NODES * 1e6 / us1, "unit": UNIT, "iters_per_sec": 1e6 / us1, "us_per_iter": us1,
-                  "what": "one chain alone, chain_persistent_kernel via pmp_run, 3 steps of %d iterations" % iters}
-
-    # ---- end-to-end arm: host buffers in, trace out, through the C-ABI the Python samplers call ----------------------
+    # ---- the same chain end to end: host buffers in, trace out, through the C-ABI the Python samplers call ----------------------
+    ctx.trace_config(iters, WHAT)
+    out_buf = ctx.trace_buffers(pinned=True)
     e2e_s = []
-    for c in ctxs:
-        c.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS)
-    outs = [c.trace_buffers(pinned=True) for c in ctxs]            # page-locked host buffers the traces are copied into
     for s in range(2 + args.steps):
         barrier()
         t0 = time.perf_counter()
-        pdist.set_data_linear_sharded(ctx, xp, yp)                 # H2D: this rank's shard of x and y (the other chains alias it)
-        for c in ctxs[1:]:
-            c.share_data_from(ctx)
-        reset(7)
-        for c in ctxs:
-            c.trace_config(iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS)
-        run_step(False)
-        trs = [c.read_trace(out=o) for c, o in zip(ctxs, outs)]                        # D2H per chain: states [iters,3] f32, accepted index [iters] i32, the P resampled indices [iters,P] i32
+        pdist.set_data_linear_sharded(ctx, xp, yp)                 # H2D: this rank's shard of x and y
+        ctx.set_state([1, 1, 1]); ctx.seed(7, 0)
+        ctx.trace_config(iters, WHAT)
+        ctx.run(iters)
+        tr = ctx.read_trace(out=out_buf)                          # D2H: states [iters,3] f32, accepted index [iters] i32, the P resampled indices [iters,P] i32
         dt = max_over_ranks(time.perf_counter() - t0)
-        assert all(tr["n"] == iters for tr in trs)
+        assert tr["n"] == iters
         if s >= 2:
             e2e_s.append(dt)
-    e2e_value = args.steps * iters * chains * P_NODES / sum(e2e_s)
-    h2d = int((hi - lo) * 8 + 12 * chains)
-    d2h = int(chains * iters * (16 + 4 * P_NODES))
-    for c in ctxs:
-        c.trace_config(0, 0)
+    e2e_value = args.steps * iters * P_NODES / sum(e2e_s)
+    h2d = int((hi - lo) * 8 + 12)
+    d2h = int(iters * (16 + 4 * P_NODES))
 
-    # ---- roofline of the dominant kernel: algorithmic flops / average launch duration ----------------------------------
-    # Single GPU: the whole chain is ONE cooperative launch (chain_persistent_kernel: 147 sweep CTAs + 1 acceptance CTA), so
-    # "the kernel's launch duration" is the timed region itself and the fraction below charges the sweep's roofline with the
-    # acceptance and the two hand-offs per iteration as well.  Multi-GPU: the stepwise loop, dominant kernel = sweep_linear_kernel.
-    flops_per_iter = 6.0 * (hi - lo) * P_NODES                   # 3 FP32 lane-ops (sub, fma, fma) per (node, point), DESIGN.md §4
+    # ---- parity at this --gpus N: chain 0's trace == the same chain run alone, un-sharded, on one GPU ---------------------------
+    hash_iters = 200
+    ctx.set_state([1, 1, 1]); ctx.seed(2024, 0); ctx.trace_config(hash_iters, WHAT)
+    ctx.run(hash_iters)
+    digest = trace_digest(ctx.read_trace())
+    parity = {"iters": hash_iters, "trace_sha256": digest, "what": "sha256 over chain 0's accepted indices and states, seed 2024, first %d iterations" % hash_iters}
+    if world > 1:
+        solo = pm.Context(local)                                  # world_size 1: the whole dataset on this GPU, no exchange
+        configure(solo)
+        solo.set_data_linear(x, y); solo.set_state([1, 1, 1]); solo.seed(2024, 0); solo.trace_config(hash_iters, WHAT)
+        solo.run(hash_iters)
+        d1 = trace_digest(solo.read_trace())
+        solo.close()
+        assert d1 == digest, "sharded chain differs from the single-GPU chain: %s vs %s" % (digest, d1)
+        parity["sharded_equals_single_gpu"] = True
+    ctx.trace_config(0, 0)
+
+    # ---- K independent chains co-scheduled in one cooperative kernel (per GPU; sharded like the single chain when N > 1) --------
+    co = None
+    chains = max(2, min(32, args.chains))
+    if "co" not in skip:
+        ctxs = [ctx]
+        for k in range(1, chains):
+            c = pdist.create_context(local)
+            configure(c)
+            c.share_data_from(ctx)
+            ctxs.append(c)
+        fused_multi = world > 1 and all(c.peers_attached for c in ctxs) and os.environ.get("PMP_PEER_XCHG", "1") != "0"
+
+        def reset(seed0):
+            for k, c in enumerate(ctxs):
+                c.set_state([1, 1, 1]); c.seed(seed0 + k, 0)
+        reset(2024)
+        for c in ctxs:
+            c.trace_config(hash_iters, WHAT)
+        L.run_multi(ctxs, hash_iters)
+        d_co = trace_digest(ctxs[0].read_trace())
+        assert d_co == digest, "co-scheduled chain 0 differs from the chain run alone: %s vs %s" % (d_co, digest)
+        parity["co_scheduled_chain0_equals_solo"] = True
+        for c in ctxs:
+            c.trace_config(0, 0)
+        reset(2024)
+        for _ in range(max(1, args.warmup - 1)):
+            ctx.l2_flush(); L.run_multi(ctxs, iters)
+        co_ms = []
+        for _ in range(args.steps):
+            ctx.l2_flush()
+            barrier(ctxs)
+            co_ms.append(max_over_ranks(L.run_multi_timed(ctxs, iters)))
+        barrier(ctxs)
+        launches += 0                                              # (co-scheduled launches are reported inside the block)
+        co_iters_per_s = args.steps * iters * chains / (sum(co_ms) * 1e-3)
+        co = {"chains": chains, "value": co_iters_per_s * P_NODES, "unit": UNIT, "iters_per_sec": co_iters_per_s, "us_per_chain_iter": 1e6 / co_iters_per_s,
+              "ms_per_step": float(np.mean(co_ms)), "vs_single_chain": co_iters_per_s / iters_per_s,
+              "what": "%d independent chains of the headline shape per GPU in one cooperative kernel (pmp_run_multi)%s; value counts all chains; every chain's trace is bit-identical to the chain run alone (parity.co_scheduled_chain0_equals_solo, tests/test_gpu_multichain.py)"
+                      % (chains, ", rows sharded over the ranks, per-node sums exchanged through NVLink peer memory inside the kernel" if fused_multi else (", rows sharded, NCCL between kernels" if world > 1 else ""))}
+        for c in reversed(ctxs[1:]):
+            c.close()
+
+    # ---- roofline of the dominant kernel: algorithmic flops / average launch duration ------------------------------------------
+    # The whole chain is ONE cooperative launch per step (chain_persistent_kernel: sweep CTAs + acceptance CTA), so "the kernel's launch
+    # duration" is the timed region itself and the fraction charges the sweep's roofline with the acceptance and the two hand-offs per
+    # iteration as well.
+    flops_per_iter = 6.0 * (hi - lo) * P_NODES                   # 3 FP32 lane-ops (sub, fma, fma) per (node, point), DESIGN.md 4
     peak = max(ctx.fp32_peak(False), ctx.fp32_peak(True))         # measured FFMA/FFMA2 issue-rate microbenchmark (MEASURED_PEAKS.json has no FP32 figure)
+    configure(ctx)
+    pdist.set_data_linear_sharded(ctx, xp, yp)
     ctx.set_state([1, 1, 1]); ctx.seed(2024, 0); ctx.propose()
     reps = 200
     sweep_ms = ctx.time_sweep(reps) / reps
     sweep_achieved = flops_per_iter / (sweep_ms * 1e-3) / 1e12
     bytes_per_iter = 8.0 * (hi - lo) + 12.0 * P_NODES + 8.0 * P_NODES
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    persistent = world == 1 and os.environ.get("PMP_PERSISTENT", "1") != "0"
-    iter_s = total_s / (args.steps * iters * chains)               # seconds per chain iteration
-    traffic = None
-    if chains > 1 and (world == 1 or fused_multi):
-        kernel, kernel_us, launch_flops = "chain_persistent_multi_kernel<MP> (%d chains, one launch per step)" % chains, iter_s * 1e6 * iters * chains, flops_per_iter * iters * chains
-        traffic = NCU_DRAM_BYTES_PER_LAUNCH_MULTI if world == 1 else None
-    elif persistent:
-        kernel, kernel_us, launch_flops = "chain_persistent_kernel<MP> (one launch per step)", iter_s * 1e6 * iters, flops_per_iter * iters
-        traffic = NCU_DRAM_BYTES_PER_LAUNCH
-    else:
-        kernel, kernel_us, launch_flops = "sweep_linear_kernel<4,true>", sweep_ms * 1e3, flops_per_iter
-    achieved = launch_flops / (kernel_us * 1e-6) / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+    iter_s = 1.0 / iters_per_s
+    kernel = ("chain_persistent_multi_kernel<MP> with one chain (sharded rows, in-kernel NVLink exchange; one launch per step)" if world > 1
+              else "chain_persistent_kernel<MP> (one launch per step)")
+    achieved = flops_per_iter / iter_s / 1e12
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "traffic_note": "not captured in this run; ncu --set full of this launch: profiles/ (dram read+write ~0.9 MB per launch: the dataset is read once and then lives in shared memory)",
                 "peak_source": "measured in this run by pmp_fp32_peak (FFMA/FFMA2 microbenchmark); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "note": "the sweep is bound by FP32 issue (3 lane-ops per node-point pair), not by HBM (0.8 MB, L2/shared-memory resident) nor by the tensor pipe; see DESIGN.md 4",
-                "kernel": kernel, "kernel_us": kernel_us, "flops_per_launch": launch_flops,
+                "kernel": kernel, "kernel_us": iter_s * 1e6 * iters, "flops_per_launch": flops_per_iter * iters,
                 "sweep_kernel_alone": {"kernel": "sweep_linear_kernel<4,true>", "kernel_us": sweep_ms * 1e3, "achieved": sweep_achieved, "frac": sweep_achieved / peak,
                                        "what": "the stepwise loop's sweep kernel launched back to back (CUDA events on the ctx stream)"},
                 "hbm": {"achieved_gbs": bytes_per_iter / iter_s / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "note": "0.8 MB of data per iteration: L2-resident, HBM is not the bound"}}
+    if co is not None:
+        co_tf = flops_per_iter * co["iters_per_sec"] / 1e12
+        co["roofline"] = {"bound": "fp32", "achieved": co_tf, "peak": peak, "unit": "TFLOP/s", "frac": co_tf / peak,
+                          "kernel": "chain_persistent_multi_kernel<MP> (%d chains, one launch per step)" % chains}
 
-    line = None
+    extras = {}
+    if world == 1:
+        if "n500" not in skip:
+            extras["n500"] = extra_n500(pm, L, local, peak)
+        if "pmp" not in skip:
+            extras["pmp_binary_d10"] = extra_pmp_binary(pm, L, local, x, y, peak, iters)
+        if "analytic" not in skip:
+            extras["analytic"] = extra_analytic(pm, L, local, hbm_peak)
+    if "fc" not in skip:
+        extras["fc"] = extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, 2)
+
     if rank == 0:
         cpu = None
-        if world == 1:
-            v, cores, dt = cpu_port_evals_per_s(x, y, 40960)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "40960 proposal-evaluations at n=100000 (40 sweeps of P=1024) with the lb.py per-proposal torch loop, %.1f s" % dt,
+        if world == 1 and "cpu" not in skip:
+            v, cores, dt, kind = cpu_sweep_evals_per_s(x, y, 20480)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "20480 proposal-evaluations at n=100000 (20 sweeps of P=1024) with %s, %.1f s" % (
+                       "the reference's own lb.py loop `net.loglik(data)` per proposal (staged unmodified copy)" if kind == "reference" else "the oracle port of the lb.py per-proposal torch loop", dt),
+                   "full_step": cpu_full_step(x, y, 32),
                    "reference_cuda_kernel_same_gpu": reference_cuda_kernel(x, y, P_NODES)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": value / BASELINE_EVALS_PER_S, "dtype": "f32", "data": "synthetic",
-                "iters_per_sec": iters_per_s, "us_per_iter": 1e6 / iters_per_s, "single_chain": single,
-                "config": {"workload": "simple_net linear-Gaussian multi-proposal MCMC (100000_MP.cu shape): P=1024 nodes, n=%d points, flat proposals alpha=0.01, SCALE=1000, CUDA draw rule; "
-                                       "%d independent chain(s) per GPU%s" % (n_global, chains, (" co-scheduled in one cooperative kernel (pmp_run_multi)" if world == 1 else
-                                                                   (" co-scheduled in one cooperative kernel per GPU, data rows sharded over the ranks, per-node sums exchanged through NVLink peer memory inside the kernel (pmp_run_multi)" if fused_multi
-                                                                    else " on separate streams and NCCL communicators, data sharded over the ranks (pmp_run_multi)")) + "; iters_per_sec and value count all chains" if chains > 1 else ""),
-                           "P": P_NODES, "n": n_global, "chains": chains, "iters_per_step": iters, "device": info["name"],
+                "iters_per_sec": iters_per_s, "us_per_iter": 1e6 / iters_per_s,
+                "config": {"workload": "simple_net linear-Gaussian multi-proposal MCMC (100000_MP.cu shape): ONE chain, P=1024 nodes, n=%d points%s, flat proposals alpha=0.01, SCALE=1000, CUDA draw rule"
+                                       % (n_global, " sharded over %d GPUs" % world if world > 1 else ""),
+                           "P": P_NODES, "n": n_global, "chains": 1, "iters_per_step": iters, "device": info["name"],
                            "l2": "flushed (256 MB memset) between steps; inside a step the dataset is re-read from L2 by design",
-                           "baseline": "reference README.md:44, V100: (33473.53 + 1099.258) us per iteration at P=1024, n=100000"},
+                           "baseline": "reference README.md:44: (33473.53 + 1099.258) us per iteration at P=1024, n=100000, one chain; README says A100, the shipped .nvvp files say V100-SXM2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "what": "set_data (pinned host x,y) + per chain: set_state, seed, %d iterations, read_trace (states, accepted indices and all P resampled indices per iteration); %d chain(s) per step, wall clock" % (iters, chains)},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                        "what": "set_data (pinned host x,y) + set_state, seed, %d iterations, read_trace (states, accepted indices and all P resampled indices per iteration); one chain, wall clock" % iters},
+                "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "co_scheduled": co, "cpu_baseline": cpu}
+        line.update(extras)
         print(json.dumps(line))
-    for c in reversed(ctxs):
-        c.close()
+    ctx.close()
     if world > 1:
         td.destroy_process_group()
 

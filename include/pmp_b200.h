@@ -161,7 +161,7 @@ int pmp_run(pmp_ctx* ctx, int64_t iters, int sync);
 int pmp_sync(pmp_ctx* ctx);
 
 /* Co-scheduled chains.  A single chain is a dependency loop (sweep on all SMs → acceptance on one → next sweep), so the sweep
- * SMs idle while their chain is being accepted.  pmp_run_multi runs n_ctx (<= 8) INDEPENDENT chains — one pmp_ctx each: own
+ * SMs idle while their chain is being accepted.  pmp_run_multi runs n_ctx (<= 32) INDEPENDENT chains — one pmp_ctx each: own
  * state, Philox key, trace — in one cooperative kernel, sweeping chain B while chain A is accepted.  Each chain's results are
  * bit-identical to the same ctx run alone with pmp_run.  Requirements: one device, world_size 1, linear-Gaussian target, the
  * same tree / algo in every ctx, and every ctx sharing ctxs[0]'s device copy of the data (pmp_share_data: dst aliases src's

@@ -1,6 +1,7 @@
 """ref_loader.py — import the REFERENCE's own Python definitions from /root/reference.  TEST INFRASTRUCTURE ONLY.
 
-Works only where the reference tree is mounted (the build container); nothing on the GPU box may call it.  The reference
+The full tree exists only in the build container; `make -C oracle` stages the few Python scripts this loader reads, unmodified, into
+oracle/_ref/pysrc (git-ignored), which travels to the GPU box — only bench.py's reference arm / cpu_baseline leg uses them there.  The reference
 scripts run experiments at import time, so only their definition part is exec'd: lb.py lines 1-376,
 error.py 1-190, com_dim.py 1-86; matplotlib (absent here) is stubbed.  Used by oracle/make_golden.py to pin
 oracle/oracle.py and pmp_oracle.c against the real code, and by the CPU test-suite when the tree is present."""
@@ -8,11 +9,20 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pysrc")   # oracle/Makefile `stage`: unmodified copies of the scripts
 REF = os.environ.get("PMP_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(REF) and os.path.isdir(_STAGED):
+    REF = _STAGED          # the GPU box: only the staged Python files travel (enough for load_lb / load_error / load_com_dim / load_fc)
 
 
 def available():
-    return os.path.isdir(REF)
+    """The full reference tree (data files, notebooks, checkpoints) — needed by make_golden.py."""
+    return os.path.isdir(REF) and REF != _STAGED
+
+
+def python_available():
+    """The reference's Python definitions (the mounted tree or the staged copies) — enough for the bench's reference arm."""
+    return os.path.isfile(os.path.join(REF, "simple_net", "lb.py"))
 
 
 def _stub_matplotlib():

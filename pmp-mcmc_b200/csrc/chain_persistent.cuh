@@ -19,6 +19,7 @@
 namespace pmp {
 
 constexpr int PERSIST_THREADS = 1024;
+constexpr int PERSIST_MAX_SEGS = 3;      // (node tile, chunk range) segments a sweep CTA keeps; the host checks the plan, the kernels trap beyond it
 constexpr int PERSIST_TP = 32, PERSIST_TD = PERSIST_THREADS / PERSIST_TP, PERSIST_R = 4, PERSIST_PT = PERSIST_TP * PERSIST_R;
 
 struct PersistSync {
@@ -84,10 +85,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
 
     // ---- stage this CTA's data slice once: segment s covers chunks [c_begin, c_end) of node tile ptile -----------------
-    int nseg = 0; int seg_tile[3]; long long seg_c0[3], seg_c1[3]; int seg_slot[3];
+    int nseg = 0; int seg_tile[PERSIST_MAX_SEGS]; long long seg_c0[PERSIST_MAX_SEGS], seg_c1[PERSIST_MAX_SEGS]; int seg_slot[PERSIST_MAX_SEGS];
     {
         long long u = u_begin; int slot = 0;
-        while (u < u_end && nseg < 3) {
+        while (u < u_end && nseg < PERSIST_MAX_SEGS) {
             int ptile = (int)(u / a.nchunks);
             long long c0 = u - (long long)ptile * a.nchunks, c1 = min(a.nchunks, c0 + (u_end - u));
             seg_tile[nseg] = ptile; seg_c0[nseg] = c0; seg_c1[nseg] = c1; seg_slot[nseg] = slot;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
             }
             slot += (int)(c1 - c0); u += c1 - c0; ++nseg;
         }
+        if (u < u_end) __trap();               // units would be dropped silently: the host-side plan (persist_segments_fit) must have refused this shape
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();

@@ -17,7 +17,8 @@
 
 namespace pmp {
 
-constexpr int PERSIST_MAX_CHAINS = 8;
+constexpr int PERSIST_MAX_CHAINS = 32;     // chains per launch (kernel parameters: ~0.6 KB per chain, 32 KB limit)
+constexpr int PERSIST_MAX_ACCEPT = 24;     // acceptance CTAs per launch (the rest of the grid sweeps)
 
 constexpr int PEER_MAX_WORLD = 8;
 
@@ -167,10 +168,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
     const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
 
     // ---- stage this CTA's data slice once (all 1024 threads): segment s covers chunks [c_begin, c_end) of node tile ptile --
-    int nseg = 0; int seg_tile[3]; long long seg_c0[3], seg_c1[3]; int seg_slot[3];
+    int nseg = 0; int seg_tile[PERSIST_MAX_SEGS]; long long seg_c0[PERSIST_MAX_SEGS], seg_c1[PERSIST_MAX_SEGS]; int seg_slot[PERSIST_MAX_SEGS];
     {
         long long u = u_begin; int slot = 0;
-        while (u < u_end && nseg < 3) {
+        while (u < u_end && nseg < PERSIST_MAX_SEGS) {
             int ptile = (int)(u / nchunks);
             long long c0 = u - (long long)ptile * nchunks, c1 = min(nchunks, c0 + (u_end - u));
             seg_tile[nseg] = ptile; seg_c0[nseg] = c0; seg_c1[nseg] = c1; seg_slot[nseg] = slot;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
             }
             slot += (int)(c1 - c0); u += c1 - c0; ++nseg;
         }
+        if (u < u_end) __trap();               // see chain_persistent.cuh
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();

@@ -62,7 +62,8 @@ struct pmp_ctx {
     int device = 0, world = 1, rank = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    void* nccl_comm = nullptr;
+    void* nccl_comm = nullptr;         // created lazily (first all-reduce): chains that only ever use the in-kernel peer exchange never build a communicator
+    unsigned char nccl_id[128] = {0};  // ncclUniqueId given to pmp_create
 
     bool configured = false;
     pmp_config cfg{};

@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <memory>
+
 #include "accept.cuh"
 #include "accept_fast.cuh"
 #include "accept_lean.cuh"
@@ -65,6 +67,14 @@ static int load_nccl() {
     } while (0)
 
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+// The persistent sweep CTAs keep at most PERSIST_MAX_SEGS (node tile, chunk range) segments; a contiguous range of `per_cta` units
+// touches at most this many tiles.  The host refuses the persistent kernels when it could exceed the cap (the kernels trap if it ever does).
+static bool persist_segments_fit(long long units, int n_sweep, long long nchunks) {
+    if (units == 0 || nchunks == 0) return true;
+    const long long per_cta = (units + n_sweep - 1) / n_sweep;
+    return (per_cta + nchunks - 2) / nchunks + 1 <= PERSIST_MAX_SEGS;
+}
 
 static long long total_chunks_global(const pmp_ctx* c) { return (c->n_global + CHUNK - 1) / CHUNK + c->world; }
 static double sat_limit(const pmp_ctx* c) { return 4611686018427387904.0 / (double)(total_chunks_global(c) > 0 ? total_chunks_global(c) : 1); }
@@ -165,8 +175,20 @@ static int launch_sweep_linear(pmp_ctx* c, int generate) {
     return PMP_OK;
 }
 
+// Collective: every rank of the ctx's world must reach it at the same point of its call sequence (they do: identical host code paths).
+// Never called while the stream is being captured — run_impl builds the communicator before it starts a capture.
+static int ensure_comm(pmp_ctx* c) {
+    if (c->world <= 1 || c->nccl_comm) return PMP_OK;
+    ncclUniqueId id; memcpy(&id, c->nccl_id, sizeof(id));
+    ncclComm_t comm;
+    PMP_NCCL(g_nccl.CommInitRank(&comm, c->world, id, c->rank));
+    c->nccl_comm = comm;
+    return PMP_OK;
+}
+
 static int allreduce_acc(pmp_ctx* c) {
     if (c->world <= 1) return PMP_OK;
+    { int rc = ensure_comm(c); if (rc) return rc; }
     PMP_NCCL(g_nccl.AllReduce(c->d_acc, c->d_acc, (size_t)c->P, ncclUint64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
     return PMP_OK;
 }
@@ -227,7 +249,8 @@ static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sw
         // fused chain loop: the acceptance kernel of iteration i publishes the nodes of iteration i+1 from the normals
         // table that the sweep of iteration i filled as a side job; only the first iteration of a run (or of a captured
         // graph, which cannot know what preceded it) builds its table and nodes with the stand-alone kernels.
-        const int fused = env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c);
+        // (an empty shard launches no sweep CTAs, hence nobody to fill the normals table: that rank builds its nodes with propose_kernel — same bits)
+        const int fused = env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c) && c->n_local > 0;
         const bool chained = fused && !first_of_graph && c->z_valid_iter == (long long)c->host_iter;
         if (!chained && (rc = launch_propose(c))) return rc;
         if (sweep_begin) PMP_CUDA(cudaEventRecord(sweep_begin, c->stream));
@@ -356,10 +379,9 @@ int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* 
     if (world_size > 1) {
         PMP_REQUIRE(nccl_unique_id, "world_size > 1 needs an NCCL unique id");
         int rc = load_nccl(); if (rc) { delete c; return rc; }
-        ncclUniqueId id; memcpy(&id, nccl_unique_id, sizeof(id));
-        ncclComm_t comm;
-        PMP_NCCL(g_nccl.CommInitRank(&comm, world_size, id, rank));
-        c->nccl_comm = comm;
+        static_assert(sizeof(ncclUniqueId) == sizeof(c->nccl_id), "NCCL unique id size");
+        memcpy(c->nccl_id, nccl_unique_id, sizeof(c->nccl_id));
+        if (env_int("PMP_NCCL_EAGER", 0)) { rc = ensure_comm(c); if (rc) { delete c; return rc; } }
     }
     *out = c;
     return PMP_OK;
@@ -564,6 +586,7 @@ int pmp_large_dim_kernel_term(pmp_ctx* c);   // fc_sweep.cu: MP kernel term for 
 // internal (not in the public header): exact cross-rank sum of fixed-point partials on the ctx stream
 int pmp_allreduce_u64(pmp_ctx* c, unsigned long long* buf, size_t count) {
     if (c->world <= 1) return PMP_OK;
+    { int rc = ensure_comm(c); if (rc) return rc; }
     PMP_NCCL(g_nccl.AllReduce(buf, buf, count, ncclUint64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
     return PMP_OK;
 }
@@ -706,7 +729,7 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     const long long units = (long long)ntiles * nchunks;
     const long long max_chunks = (units + n_sweep - 1) / n_sweep + 1;
     const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
-    if (!lean_accept_ok(c)) return 0;
+    if (!lean_accept_ok(c) || !persist_segments_fit(units, n_sweep, nchunks)) return 0;
     const size_t accept_smem = lean_smem_bytes(c->P, c->cfg.algo);
     const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
     if (smem > 200 * 1024) return 0;
@@ -756,7 +779,7 @@ static int try_run_persistent_tc(pmp_ctx* c, int64_t iters) {
     const long long units = nchunks * ntiles;
     const long long per = (units + n_sweep - 1) / n_sweep;
     const long long mc = (per + ntiles - 1) / ntiles + 1;
-    if (per > tc::MAX_UNITS) return 0;
+    if (per > tc::MAX_UNITS || !persist_segments_fit(units, n_sweep, nchunks)) return 0;
     const size_t sweep_smem = tc::pt_smem_bytes(ntiles, (int)mc, (int)per), accept_smem = lean_smem_bytes(c->P, c->cfg.algo);
     const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
     if (smem > 200 * 1024) return 0;
@@ -810,6 +833,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
         rc = try_run_persistent_tc(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK;
         rc = try_run_persistent(c, iters); if (rc != 0) return rc < 0 ? rc : PMP_OK;
     }
+    if ((rc = ensure_comm(c))) return rc;             // stepwise loop with NCCL between kernels: the communicator must exist before any stream capture
     int64_t done = 0;
     if (GI > 1 && iters >= GI && c->cfg.target != PMP_TARGET_FC && c->cfg.target != PMP_TARGET_GLM_LOGISTIC && c->cfg.target != PMP_TARGET_GLM_GAUSS) {     // FC iterations are milliseconds of GEMMs: nothing to gain from a graph
         if (!c->graph_exec || c->graph_iters != GI) {
@@ -835,7 +859,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
             PMP_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
             c->launches += c->graph_launches_total;
             c->host_iter += GI;
-            c->z_valid_iter = (env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c)) ? (long long)c->host_iter : -1;
+            c->z_valid_iter = (env_int("PMP_FUSE_PROPOSE", 1) && fast_accept_ok(c) && c->n_local > 0) ? (long long)c->host_iter : -1;
         }
     }
     for (; done < iters; ++done) if ((rc = enqueue_iteration(c, nullptr, nullptr, false))) return rc;
@@ -893,15 +917,23 @@ static int run_multi_streams(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_
 }
 
 // world_size > 1: can these chains run in the cooperative kernel that exchanges the sums over NVLink peer memory?
+// Every rank must take the SAME decision (a rank in the cooperative kernel spins on its peers' tags while a rank on the NCCL path blocks
+// in ncclAllReduce), so the shape tests use rank-independent quantities only: the largest shard any rank can hold when the rows are
+// split into 64-point blocks as evenly as possible (dist.shard_bounds) — derived from n_global and world_size — never this rank's own
+// n_local.  A rank whose shard is larger than that bound fails loudly (PMP_ERR_ARG) instead of silently choosing another path.
+static long long max_shard_chunks(const pmp_ctx* c) {
+    const long long blocks = (c->n_global + CHUNK - 1) / CHUNK;
+    return (blocks + c->world - 1) / c->world;
+}
 static bool peer_fused_ok(pmp_ctx** cs, int K, int64_t iters) {
     pmp_ctx* c0 = cs[0];
     if (!env_int("PMP_PEER_XCHG", 1) || c0->world > PEER_MAX_WORLD || iters < 2 || iters > 2000000000ll || !env_int("PMP_PERSISTENT", 1)) return false;
-    const long long nchunks = (c0->n_local + CHUNK - 1) / CHUNK;
-    const int n_sweep = c0->sm_count - K;
+    const long long nchunks = max_shard_chunks(c0);
+    const int n_sweep = c0->sm_count - (K < PERSIST_MAX_ACCEPT ? K : PERSIST_MAX_ACCEPT);
     if (nchunks == 0 || n_sweep < 1) return false;
     const long long units = (long long)((c0->P + PERSIST_PT - 1) / PERSIST_PT) * nchunks;
     const size_t sweep_smem = (size_t)((units + n_sweep - 1) / n_sweep + 1) * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
-    if (sweep_smem > 200 * 1024) return false;
+    if (sweep_smem > 200 * 1024 || !persist_segments_fit(units, n_sweep, nchunks)) return false;
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
         if (!(c->peers_attached && c->cfg.target == PMP_TARGET_LINEAR_GAUSS && lean_accept_ok(c) && !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) &&
@@ -936,22 +968,26 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     PMP_CUDA(cudaSetDevice(c0->device));
     // Acceptance CTAs, up to one per chain: an acceptance is ~10 us of dependent latencies on one SM, so with fewer acceptance CTAs than chains
     // the acceptances — not the sweeps — bound the throughput as soon as a sweep is short (measured, n = 12 500, K = 8: 6.2 us per chain
-    // iteration with 2 acceptance CTAs, 2.8 us with 8).  PMP_MULTI_ACCEPT overrides (1..K).
-    int n_accept = c0->world > 1 ? K : (K < 4 ? K : 4);        // one GPU, full dataset: four suffice (10.4 vs 11.0 us per chain iteration at K = 8)
-    { const int ov = env_int("PMP_MULTI_ACCEPT", 0); if (ov >= 1 && ov <= K) n_accept = ov; }
+    // iteration with 2 acceptance CTAs, 2.8 us with 8).  PMP_MULTI_ACCEPT overrides (1..min(K, PERSIST_MAX_ACCEPT)).
+    const int acc_cap = K < PERSIST_MAX_ACCEPT ? K : PERSIST_MAX_ACCEPT;
+    int n_accept = c0->world > 1 ? acc_cap : (K < 4 ? K : (K <= 8 ? 4 : acc_cap / 2));        // one GPU, full dataset: one per two chains suffices (10.4 vs 11.0 us per chain iteration at K = 8)
+    { const int ov = env_int("PMP_MULTI_ACCEPT", 0); if (ov >= 1 && ov <= acc_cap) n_accept = ov; }
     const int G = c0->sm_count, n_sweep = G - n_accept;
+    // world > 1: the kernel's shared-memory plan follows the LARGEST shard of any rank (rank-independent, see peer_fused_ok); this rank's own
+    // shard must not exceed it.  An empty shard is fine: its sweep CTAs have no units, only arrive.
     const long long nchunks = (c0->n_local + CHUNK - 1) / CHUNK;
-    PMP_REQUIRE(nchunks > 0 && n_sweep >= 1, "no data");
+    const long long plan_chunks = c0->world > 1 ? max_shard_chunks(c0) : nchunks;
+    PMP_REQUIRE(nchunks <= plan_chunks, "this rank's shard (%lld blocks of 64 points) exceeds the even split (%lld blocks): shard with dist.shard_bounds or set PMP_PEER_XCHG=0", nchunks, plan_chunks);
+    PMP_REQUIRE(plan_chunks > 0 && n_sweep >= 1, "no data");
     const int ntiles = (c0->P + PERSIST_PT - 1) / PERSIST_PT;
-    const long long units = (long long)ntiles * nchunks;
-    const long long max_chunks = (units + n_sweep - 1) / n_sweep + 1;
+    const long long max_chunks = ((long long)ntiles * plan_chunks + n_sweep - 1) / n_sweep + 1;
+    PMP_REQUIRE(persist_segments_fit((long long)ntiles * plan_chunks, n_sweep, plan_chunks), "co-scheduled chains: a sweep CTA would span more than %d node tiles", PERSIST_MAX_SEGS);
     const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
     const size_t accept_smem = lean_smem_bytes(c0->P, c0->cfg.algo);
     const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
     if (smem > 200 * 1024) { set_error("co-scheduled chains: a sweep CTA's data slice (%zu bytes) does not fit shared memory", smem); return PMP_ERR_UNSUPPORTED; }
-    static PersistMultiArgs pa_storage;            // ~5 KB: more than the classic 4 KB kernel-parameter limit (CUDA >= 12.1 on sm_70+ allows 32 KB)
-    PersistMultiArgs& pa = pa_storage;
-    pa = PersistMultiArgs{};
+    std::unique_ptr<PersistMultiArgs> pa_owner(new PersistMultiArgs());      // per call: several host threads may drive different contexts (kernel parameters are copied at launch)
+    PersistMultiArgs& pa = *pa_owner;
     int rc;
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
@@ -966,7 +1002,6 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
         pa.ch[k].sync = reinterpret_cast<PersistSync*>(c->d_psync);
         pa.ch[k].xchg.world = c->world; pa.ch[k].xchg.me = c->rank; pa.ch[k].xchg.local = c->d_xchg; pa.ch[k].xchg.base = c->xchg_count;
         for (int r = 0; r < PEER_MAX_WORLD; ++r) pa.ch[k].xchg.peer[r] = c->peer_xchg[r];
-        if (c->world > 1) c->xchg_count += (unsigned long long)iters;
         PMP_CUDA(cudaStreamSynchronize(c->stream));                // everything queued on this chain's own stream is done before the joint launch
     }
     pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks; pa.n_accept = n_accept;
@@ -993,6 +1028,7 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
         if (k > 0) PMP_CUDA(cudaStreamWaitEvent(c->stream, c0->ev1, 0));   // later work on the chain's own stream is ordered after the joint kernel
+        if (c->world > 1) c->xchg_count += (unsigned long long)iters;       // only once the launch is in the stream: a failed launch must not shift the tags
         c->host_iter += (unsigned long long)iters;
         c->z_valid_iter = -1;
         c->lt_valid = false;

@@ -258,12 +258,16 @@ class GMpreOptimizerV2(_DeviceSampler):
         return tr["samples"].reshape(num_steps * ctx.P, 3).astype(np.float64)           # lb.py:350,364-368
 
 
-def fit_independent(trainers, data, num_steps=1000):
+MAX_CO_SCHEDULED = 32      # csrc/chain_persistent_multi.cuh: PERSIST_MAX_CHAINS
+
+
+def fit_independent(trainers, data, num_steps=1000, max_group=MAX_CO_SCHEDULED):
     """Independent chains co-scheduled in one cooperative kernel (pmp_run_multi).
 
     The reference runs its experiments as independent repeats — error.py:191-213 (20 repeats per sampler), lb.py:377-423 (one
-    chain per step size) — one after the other.  Here up to 8 `GMOptimizer` (or up to 8 `preMOptimizer`) trainers with the same
-    N run at once: one chain alone leaves the sweep SMs idle while it is being accepted.  Every trainer keeps its own seed,
+    chain per step size) — one after the other.  Here up to 32 `GMOptimizer` (or `preMOptimizer`) trainers with the same
+    N run at once (more are run in groups of `max_group`; every group aliases the one device copy of the data that the first
+    trainer's context owns): one chain alone leaves the sweep SMs idle while it is being accepted.  Every trainer keeps its own seed,
     step size and start state, gets exactly the trace `trainer.fit(data, num_steps)` would return (bit for bit), and ends in
     the same state.  Returns the list of traces in trainer order."""
     trainers = list(trainers)
@@ -290,9 +294,13 @@ def fit_independent(trainers, data, num_steps=1000):
         ctx.trace_config(num_steps, what)
         ctxs.append(ctx)
     out = []
-    for lo in range(0, len(ctxs), 8):
-        group = ctxs[lo:lo + 8]
-        L.run_multi(group, num_steps)
+    max_group = max(1, min(int(max_group), MAX_CO_SCHEDULED))
+    for lo in range(0, len(ctxs), max_group):
+        group = ctxs[lo:lo + max_group]
+        if len(group) == 1:
+            group[0].run(num_steps)                          # a leftover chain runs alone: same bits (tests/test_gpu_multichain.py)
+        else:
+            L.run_multi(group, num_steps)
     for t, ctx in zip(trainers, ctxs):
         tr = ctx.read_trace()
         t._iteration += num_steps

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--points", dest="n", type=int, default=30000)
     ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--chains", type=int, default=2)
     a = ap.parse_args()
     import torch
     import torch.distributed as td
@@ -83,33 +84,35 @@ def main():
         assert torch.equal(t, ref)
         for k in ("state", "next", "draws", "logw"):
             res[name + "_" + k] = tr[k]
-    # two sharded chains on two streams / two communicators (pmp_run_multi, streams mode): chain 0 repeats the "mp" run above,
-    # chain 1 is an independent chain with its own key — each must equal its solo run
-    ctx2 = pdist.create_context(local)
-    for c, seed in ((ctx, 99), (ctx2, 123)):
+    # K sharded chains (pmp_run_multi): chain 0 repeats the "mp" run above, the others are independent chains with their own keys — each
+    # must equal its solo run.  fused: one cooperative kernel per GPU, sums exchanged through NVLink peer memory inside it (all K chains);
+    # streams: NCCL between kernels, one stream + communicator per chain (first 4 chains)
+    K = max(2, a.chains)
+    ctxs = [ctx] + [pdist.create_context(local) for _ in range(K - 1)]
+    for c in ctxs:
         c.configure(0, b=256, depth=1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.02, scale=1000.0)
     pdist.set_data_linear_sharded(ctx, x, y)
-    ctx2.share_data_from(ctx)
-    for c, seed in ((ctx, 99), (ctx2, 123)):
-        c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
-        c.trace_config(a.iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW)
-    # fused: one cooperative kernel per GPU, sums exchanged through NVLink peer memory inside it; streams: NCCL between kernels
-    for mode, tags in (("1", ("co0", "co1")), ("0", ("st0", "st1"))):
+    for c in ctxs[1:]:
+        c.share_data_from(ctx)
+    for mode, prefix, group in (("1", "co", ctxs), ("0", "st", ctxs[:min(K, 4)])):
         os.environ["PMP_PEER_XCHG"] = mode
-        for c, seed in ((ctx, 99), (ctx2, 123)):
-            c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
+        for k, c in enumerate(group):
+            c.set_state([-0.8, 1.7, 0.7]); c.seed(99 + 24 * k, 0)
             c.trace_config(a.iters, L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW)
-        L.run_multi([ctx, ctx2], a.iters)
-        for tag, c in zip(tags, (ctx, ctx2)):
+        L.run_multi(group, a.iters)
+        for k, c in enumerate(group):
             tr = c.read_trace()
             t = torch.from_numpy(tr["draws"].copy()).cuda()
             ref = t.clone(); td.broadcast(ref, src=0)
             assert torch.equal(t, ref)                       # replicated acceptance: identical on every rank
-            for k in ("state", "next", "draws", "logw"):
-                res[tag + "_" + k] = tr[k]
+            for key in ("state", "next", "draws", "logw"):
+                res["%s%d_%s" % (prefix, k, key)] = tr[key]
     os.environ["PMP_PEER_XCHG"] = "1"
-    L.run_multi([ctx, ctx2], a.iters)                       # a second fused launch continues the exchange counters
-    assert ctx.iteration() == 2 * a.iters and ctx2.iteration() == 2 * a.iters
+    it0 = ctx.iteration()
+    L.run_multi(ctxs, a.iters)                              # a second fused launch continues the exchange counters
+    assert all(c.iteration() == it0 + a.iters for c in ctxs[:min(K, 4)])
+    for c in reversed(ctxs[1:]):
+        c.close()
     # FC and GLM sweeps on sharded rows: integer loss sums all-reduced inside the library → the same bits as one GPU
     from oracle import oracle as o
     rng = np.random.default_rng(31)
@@ -130,7 +133,6 @@ def main():
     res["glm_lt"] = ctx.loglik()
     if rank == 0:
         np.savez(a.out, world=world, **res)
-    ctx2.close()
     ctx.close()
     td.destroy_process_group()
 

@@ -124,3 +124,52 @@ def test_fc_device_resident_run_equals_stepwise(ctx):
     tr = ctx.read_trace()
     assert list(tr["next"]) == nxts and np.array_equal(ctx.get_state(), ref) and ctx.iteration() == 4
     ctx.trace_config(0, 0)
+
+
+@pytest.mark.parametrize("tag", ["s", "full"])
+@pytest.mark.parametrize("kind", ["PMP", "MP"])
+def test_fc_trained_model_accepted_index_is_the_references(ctx, kind, tag):
+    """theta0 = the reference's FC_model.pkl, alpha = 1e-4 (PMP_FC.py:15,188-189), n = 384 and the BASELINE size n = 60 000: the device's
+    losses against the reference's float32 loss(net), its standardised weights against the reference's B, and — for every injected uniform
+    whose distance to a boundary of the reference's cdf exceeds the measured cdf discrepancy — the SAME accepted index as the reference's
+    PMPOptimizer.step / MPOptimizer.step (tests/golden/fc_step_trained.npz, generated from the reference's own code)."""
+    import os
+    from conftest import ROOT
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    G = np.load(os.path.join(ROOT, "tests", "golden", "fc_step_trained.npz"))
+    theta0 = np.load(os.path.join(ROOT, "tests", "golden", "fc_theta0.npy"))
+    n = int(G[tag + "_n"])
+    X = np.random.default_rng(int(G[tag + "_data_seed"])).standard_normal((n, 28, 28)).astype(np.float32)
+    y = G[tag + "_labels"].astype(np.int64)
+    if kind == "PMP":
+        ctx.configure(L.TREE_BINARY, depth=3, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=float(G["alpha"]), scale=10.0)
+    else:
+        ctx.configure(L.TREE_FLAT, b=8, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_MP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE | L.FLAG_KERNEL_MEAN, alpha=float(G["alpha"]), scale=10.0)
+    ctx.set_data_fc(X.reshape(n, -1), y)
+
+    def fresh():
+        ctx.set_state(theta0); ctx.seed(int(G["prop_seed"]), 0); ctx.propose()
+        return ctx.loglik()
+    lt = fresh()
+    ref_loss, truth = G["%s_%s_loss" % (tag, kind)], G["%s_%s_truth" % (tag, kind)]
+    np.testing.assert_allclose(-lt, ref_loss, rtol=2e-5)
+    # node differences (what the standardised weights are made of): ~1e-5 of the loss here; resolved to 5 % of the largest one
+    d_dev, d_true = (-lt)[1:] - (-lt)[0], truth[1:] - truth[0]
+    assert np.max(np.abs(d_dev - d_true)) <= 0.05 * np.max(np.abs(d_true)), (d_dev, d_true)
+    B = G["%s_%s_B" % (tag, kind)]
+    cdf_ref = np.cumsum(B / B.sum())
+    u_grid, I_ref = G["u_grid"], G["%s_%s_I" % (tag, kind)]
+    compared = 0
+    cdf_gap = None
+    for u, i_ref in zip(u_grid, I_ref):
+        fresh()
+        idx, nxt = ctx.accept(np.array([float(u)]))
+        if cdf_gap is None:
+            w = o.weights_from_log(ctx.read_logweights())
+            cdf_gap = float(np.max(np.abs(np.cumsum(w / w.sum()) - cdf_ref)))
+            assert cdf_gap < 0.03, cdf_gap            # stated bound: bf16-split contraction + float32 reference weights, after standardisation
+        if np.min(np.abs(u - cdf_ref[:-1])) > cdf_gap:      # the reference's index is well defined at this uniform
+            assert idx[0] == i_ref == nxt, (u, idx, i_ref)
+            compared += 1
+    assert compared >= 9, compared

@@ -106,6 +106,7 @@ def _ref_lib(name):
     fp = ctypes.POINTER(ctypes.c_float)
     lib.ref_set_data.argtypes = [fp, fp, ctypes.c_int]
     lib.ref_loglik.argtypes = [fp, ctypes.c_int, fp, ctypes.c_int, fp]
+    lib.ref_loglik_ex.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, fp]
     return lib
 
 
@@ -138,3 +139,78 @@ def test_against_reference_cuda_kernel(ctx, libname, n, scale, P, algo_flags):
     assert ref.ref_loglik(props.ctypes.data_as(fp), P, out.ctypes.data_as(fp), 1, ctypes.byref(ms)) == 0
     # the reference accumulates in a float32 running sum (n + P*3 roundings): 5e-5 relative at n=1e5 (see test_loglik_parity)
     np.testing.assert_allclose(A, out.astype(np.float64), rtol=5e-5 if n > 10000 else 2e-5)
+
+
+@pytest.mark.parametrize("libname,n,scale,b,D,fix", [
+    ("libref_conv_pmp.so", 100000, 2000.0, 8, 3, 0),      # conv_pmp.cu as shipped: P = 512, N_step = 7, tree_deep = 3 (conv_pmp.cu:85-87), table upload bug included
+    ("libref_conv_pmp.so", 100000, 2000.0, 8, 3, 1),      # the same kernel fed the whole table as floats: its transition arithmetic (conv_pmp.cu:22-33)
+    ("libref_conv_pmp.so", 5000, 2000.0, 4, 2, 1),
+    ("libref_conv_pmp.so", 5000, 2000.0, 3, 4, 1),
+    ("libref_pmp_500.so", 500, 10.0, 2, 6, 1),            # binary table kernel (500_PMP.cu:23-30) with the table uploaded correctly
+    ("libref_pmp_100000.so", 100000, 1000.0, 2, 10, 1),
+])
+def test_against_reference_tree_kernels(ctx, libname, n, scale, b, D, fix):
+    """General-tree kernel of conv_pmp.cu:10-36 and the binary one of 500_PMP.cu:10-33, compiled from the reference's source, with the
+    transition table rebuilt by oracle/ref_harness.cu (conv_pmp.cu:182-221) — as shipped (PMP_FLAG_QUIRK_TABLE_CONST) and with the table
+    uploaded in full (the intended rule: PMP_ALGO_TABLE without the quirk flag)."""
+    import ctypes
+    L, o = _L(), _o()
+    ref = _ref_lib(libname)
+    P = b ** D
+    x, y = synthetic_linear(n, seed=13)
+    fp = ctypes.POINTER(ctypes.c_float)
+    assert ref.ref_set_data(x.ctypes.data_as(fp), y.ctypes.data_as(fp), n) == 0
+    tree = L.TREE_BINARY if b == 2 else L.TREE_BARY
+    ctx.configure(tree, b=b, depth=D, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_TABLE, draw=L.DRAW_CUDA, alpha=0.02, scale=scale,
+                  flags=0 if fix else L.FLAG_QUIRK_TABLE_CONST)
+    ctx.set_data_linear(x, y)
+    ctx.set_state([0, 0, 1] if b != 2 else [1, 1, 1]); ctx.seed(7, 0); ctx.propose()      # conv_pmp.cu:129 starts at (0, 0, 1)
+    props = ctx.read_proposals()
+    ctx.loglik(read=False)
+    ctx.accept(np.full(P, 0.5))
+    A = ctx.read_logweights()
+    out = np.zeros(P, dtype=np.float32)
+    ms = ctypes.c_float()
+    assert ref.ref_loglik_ex(props.ctypes.data_as(fp), P, D, b - 1, fix, out.ctypes.data_as(fp), 1, ctypes.byref(ms)) == 0
+    np.testing.assert_allclose(A, out.astype(np.float64), rtol=5e-5 if n > 10000 else 2e-5)
+    # and the oracle's restatement of the same rule agrees with the reference kernel too
+    lt = o.loglik_linear_f64(x, y, props, scale)
+    np.testing.assert_allclose(o.table_logweights(lt, props.astype(np.float64), b, D, quirk_const=not fix), out.astype(np.float64), rtol=5e-5 if n > 10000 else 2e-5)
+
+
+def test_against_reference_mh_and_conv_mp_kernels(ctx):
+    """conv_mh.cu:10-26 (<<<1,1>>>, two hard-coded candidates, /2000) and conv_mp.cu's MP kernel (N = 7, /2000) compiled from source."""
+    import ctypes
+    L, o = _L(), _o()
+    fp = ctypes.POINTER(ctypes.c_float)
+    n = 100000
+    x, y = synthetic_linear(n, seed=17)
+    # MH: A[0], A[1] are the two log-likelihoods / 2000; the device MH rule accepts iff u < exp(A1 - A0) (conv_mh.cu:152)
+    ref = _ref_lib("libref_conv_mh.so")
+    assert ref.ref_set_data(x.ctypes.data_as(fp), y.ctypes.data_as(fp), n) == 0
+    ctx.configure(L.TREE_FLAT, b=2, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MH, draw=L.DRAW_CUDA, alpha=0.02, scale=2000.0)
+    ctx.set_data_linear(x, y)
+    ctx.set_state([0, 0, 1]); ctx.seed(3, 0); ctx.propose()
+    props = ctx.read_proposals()
+    lt = ctx.loglik()
+    out = np.zeros(2, dtype=np.float32)
+    ms = ctypes.c_float()
+    assert ref.ref_loglik_ex(props.ctypes.data_as(fp), 2, 1, 1, 0, out.ctypes.data_as(fp), 1, ctypes.byref(ms)) == 0
+    np.testing.assert_allclose(lt, out.astype(np.float64), rtol=5e-5)
+    ratio = np.exp(float(out[1]) - float(out[0]))
+    for u in (0.999 * min(ratio, 1.0), min(1.0 - 1e-9, 1.001 * ratio)):
+        ctx.set_state([0, 0, 1]); ctx.seed(3, 0); ctx.propose(); ctx.loglik(read=False)
+        idx, nxt = ctx.accept(np.array([u]))
+        assert nxt == (1 if u < np.exp(lt[1] - lt[0]) else 0)
+    # MP, conv_mp.cu shape
+    ref = _ref_lib("libref_conv_mp.so")
+    assert ref.ref_set_data(x.ctypes.data_as(fp), y.ctypes.data_as(fp), n) == 0
+    ctx.configure(L.TREE_FLAT, b=8, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.02, scale=2000.0)
+    ctx.set_data_linear(x, y)
+    ctx.set_state([0, 0, 1]); ctx.seed(4, 0); ctx.propose()
+    props = ctx.read_proposals()
+    ctx.loglik(read=False); ctx.accept(np.full(8, 0.5))
+    A = ctx.read_logweights()
+    out = np.zeros(8, dtype=np.float32)
+    assert ref.ref_loglik_ex(props.ctypes.data_as(fp), 8, 1, 1, 0, out.ctypes.data_as(fp), 1, ctypes.byref(ms)) == 0
+    np.testing.assert_allclose(A, out.astype(np.float64), rtol=5e-5)

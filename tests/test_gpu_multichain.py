@@ -21,7 +21,7 @@ def _configure(c, L, k):
 
 
 @pytest.mark.parametrize("name,k", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("n_chains", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 4, 8, 13, 32])
 def test_co_scheduled_chains_equal_solo_chains(name, k, n_chains):
     import pmp_mcmc_b200 as pm
     from pmp_mcmc_b200 import _lib as L
@@ -30,7 +30,7 @@ def test_co_scheduled_chains_equal_solo_chains(name, k, n_chains):
     what = L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW
     rs = np.random.default_rng(17)
     starts = [np.array([0.0, 0.0, 1.0], np.float32), np.array([-1.0, 2.0, 0.5], np.float32)] + \
-             [np.array([rs.uniform(-1, 1), rs.uniform(-1, 2), rs.uniform(0.5, 2)], np.float32) for _ in range(6)]
+             [np.array([rs.uniform(-1, 1), rs.uniform(-1, 2), rs.uniform(0.5, 2)], np.float32) for _ in range(30)]
     solo = []
     for i in range(n_chains):
         c = pm.Context(0)
@@ -94,3 +94,52 @@ def test_fit_independent_equals_fit():
     traces = S.fit_independent(trainers, data, 30)
     for (ref, th), tr, t in zip(solo, traces, trainers):
         assert tr.shape == (30 * 8, 3) and np.array_equal(tr, ref) and np.array_equal(t.net.theta(), th)
+
+
+def test_fit_independent_in_groups():
+    """More trainers than one launch takes: groups of `max_group` chains, every group aliasing the first trainer's data; a leftover single
+    chain runs alone.  Each trainer still gets its own fit() trace."""
+    from pmp_mcmc_b200 import samplers as S
+    x, y = synthetic_linear(3000, seed=9)
+    data = {"x": x, "y": y}
+    alphas = [0.01 * (1 + k) for k in range(10)]
+    solo = []
+    for k, alpha in enumerate(alphas):
+        t = S.preMOptimizer(S.BayesNet(), alpha, N=7, seed=70 + k)
+        solo.append(t.fit(data, 12))
+    trainers = [S.preMOptimizer(S.BayesNet(), alpha, N=7, seed=70 + k) for k, alpha in enumerate(alphas)]
+    traces = S.fit_independent(trainers, data, 12, max_group=3)          # 3 + 3 + 3 + 1
+    for ref, tr in zip(solo, traces):
+        assert np.array_equal(tr, ref)
+
+
+def test_headline_shape_co_scheduled_equals_solo():
+    """The launch bench.py times: P = 1024 flat MP, n = 100 000, CUDA draw rule, 8 chains co-scheduled — chain 0 and chain 7 against solo runs."""
+    import pmp_mcmc_b200 as pm
+    from pmp_mcmc_b200 import _lib as L
+    n, iters, K = 100000, 60, 8
+    x, y = synthetic_linear(n, seed=0)
+    what = L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS
+
+    def make(seed, owner=None):
+        c = pm.Context(0)
+        c.configure(L.TREE_FLAT, b=1024, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.01, scale=1000.0)
+        if owner is None:
+            c.set_data_linear(x, y)
+        else:
+            c.share_data_from(owner)
+        c.set_state([1, 1, 1]); c.seed(seed, 0); c.trace_config(iters, what)
+        return c
+    ctxs = [make(2024)]
+    ctxs += [make(2024 + k, ctxs[0]) for k in range(1, K)]
+    L.run_multi(ctxs, iters)
+    got = [c.read_trace() for c in ctxs]
+    for k in (0, K - 1):
+        s = make(2024 + k)
+        s.run(iters)
+        ref = s.read_trace()
+        for key in ("state", "next", "draws"):
+            assert np.array_equal(got[k][key], ref[key]), (k, key)
+        s.close()
+    for c in reversed(ctxs):
+        c.close()

@@ -10,10 +10,20 @@ import pytest
 from conftest import ROOT, synthetic_linear
 
 
-def _torchrun(nproc, args, port):
+def _torchrun(nproc, args, port, timeout=500):
+    """torchrun in its own process group; on a timeout the WHOLE group is killed (a hung rank must not keep spinning on the GPU)."""
+    import signal
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu_worker.py")] + args
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=500)
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        out, err = p.communicate()
+        err += "\n[killed after %d s]" % timeout
+        return subprocess.CompletedProcess(cmd, -9, out, err)
+    return subprocess.CompletedProcess(cmd, p.returncode, out, err)
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -36,17 +46,21 @@ def test_shard_bounds_properties():
 
 
 @pytest.mark.gpu
-def test_sharded_chain_equals_single_gpu_chain(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_chain_equals_single_gpu_chain(tmp_path, world):
+    """Sharded over `world` GPUs — a single chain, K = 8 chains co-scheduled in the fused peer-exchange kernel, 4 chains on streams +
+    NCCL communicators (PMP_PEER_XCHG=0) — every trace must equal the same chain run alone on ONE GPU, bit for bit."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs >= %d GPUs (run under gpurun --gpus %d)" % (world, world))
     import pmp_mcmc_b200 as pm
     from pmp_mcmc_b200 import _lib as L
-    n, iters = 30000, 40
+    n, iters, K = 30000, 40, 8
     out = tmp_path / "mg.npz"
-    r = _torchrun(2, ["--out", str(out), "--points", str(n), "--iters", str(iters)], 29633)
+    r = _torchrun(world, ["--out", str(out), "--points", str(n), "--iters", str(iters), "--chains", str(K)], 29633 + world)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     g = np.load(out)
+    assert int(g["world"]) == world
     x, y = synthetic_linear(n, seed=21)
     c = pm.Context(0)
     try:
@@ -59,8 +73,10 @@ def test_sharded_chain_equals_single_gpu_chain(tmp_path):
             tr = c.read_trace()
             for k in ("state", "next", "draws", "logw"):      # integer-exact partial sums → identical bits at any GPU count
                 assert np.array_equal(tr[k], g[name + "_" + k]), (name, k)
-        # two sharded chains overlapped on two streams / communicators equal their solo single-GPU runs
-        for tag, seed in (("co0", 99), ("co1", 123), ("st0", 99), ("st1", 123)):
+        # K sharded chains in the fused kernel ("co<k>") and 4 on streams / communicators ("st<k>") equal their solo single-GPU runs
+        tags = ["co%d" % k for k in range(K)] + ["st%d" % k for k in range(min(K, 4))]
+        for tag in tags:
+            seed = 99 + 24 * int(tag[2:])
             c.configure(0, b=256, depth=1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.02, scale=1000.0)
             c.set_data_linear(x, y)
             c.set_state([-0.8, 1.7, 0.7]); c.seed(seed, 0)
