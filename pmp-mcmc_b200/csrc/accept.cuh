@@ -34,6 +34,18 @@ struct ProposeArgs {
 // One thread per (node, coordinate).  The value is built along the node's ancestor chain in float32 with the
 // reference's two roundings per step: child = fl(parent + fl(alpha * z))  (normal_distribution<float>(0, alpha),
 // torch.normal(0, alpha)).  z for the step that created node `a` is normal number a*dim + j of the iteration.
+// Ancestors of `node` in creation order (root side first): f(anc) for every level whose digit is non-zero, anc = node mod b^(l+1).
+// 32-bit arithmetic, bit operations for the binary tree: this runs on the critical path of the chain (next-iteration nodes).
+template <class F>
+__device__ __forceinline__ void for_each_ancestor(int tree, int b, int depth, int node, F f) {
+    if (tree == PMP_TREE_BINARY) {
+        for (int l = 0; l < depth; ++l) if ((node >> l) & 1) f(node & ((2 << l) - 1));
+    } else {
+        int s = 1;
+        for (int l = 0; l < depth; ++l) { const int sb = s * b, m = node % sb; if (m >= s) f(m); s = sb; }
+    }
+}
+
 static __device__ __noinline__ float proposal_value(const ProposeArgs& a, unsigned long long iter, int node, int j, float v) {
     if (a.tree == PMP_TREE_FLAT) {
         if (node > 0) {
@@ -42,17 +54,10 @@ static __device__ __noinline__ float proposal_value(const ProposeArgs& a, unsign
         }
         return v;
     }
-    const int b = (a.tree == PMP_TREE_BINARY) ? 2 : a.b;
-    long long s = 1;
-    for (int l = 0; l < a.depth; ++l) {
-        long long digit = (node / s) % b;
-        if (digit != 0) {
-            long long anc = node % (s * b);
-            float z = (float)stream_step(a.seed, iter, (unsigned long long)anc * a.dim + j, a.uniform);
-            v = __fadd_rn(v, __fmul_rn(a.alpha, z));
-        }
-        s *= b;
-    }
+    for_each_ancestor(a.tree, a.b, a.depth, node, [&](int anc) {
+        float z = (float)stream_step(a.seed, iter, (unsigned long long)anc * a.dim + j, a.uniform);
+        v = __fadd_rn(v, __fmul_rn(a.alpha, z));
+    });
     return v;
 }
 
@@ -63,6 +68,25 @@ static __global__ void __launch_bounds__(256) propose_kernel(ProposeArgs a) {
         int node = (int)(g / a.dim), j = (int)(g - (long long)node * a.dim);
         a.props[g] = proposal_value(a, iter, node, j, a.state[j]);
     }
+}
+
+// Tree proposals for long parameter vectors (the FC model: 567 434 coordinates), one tree level per launch: the nodes created at level l
+// (m in [s, s*b), s = b^l) are their parents (m mod s) plus one increment — ONE quantile evaluation per element instead of one per
+// ancestor, and the same float32 operation sequence as proposal_value (child = fl(parent + fl(alpha z))), hence the same bits.
+// grid.y = new node, grid.x covers the coordinates.  Level -1 (s = 0): node 0 = the current state.
+static __global__ void __launch_bounds__(256) propose_level_kernel(ProposeArgs a, int s) {
+    const unsigned long long iter = a.cnt->iteration;
+    const long long dim = a.dim;
+    if (s == 0) {
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x) a.props[j] = a.state[j];
+        return;
+    }
+    const int m = s + blockIdx.y, parent = m % s;
+    const float* src = a.props + (long long)parent * dim;
+    float* dst = a.props + (long long)m * dim;
+    const unsigned long long base = (unsigned long long)m * dim;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x)
+        dst[j] = __fadd_rn(src[j], __fmul_rn(a.alpha, (float)stream_step(a.seed, iter, base + j, a.uniform)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -428,13 +452,7 @@ __device__ __forceinline__ float proposal_value_z(const ProposeArgs& a, const fl
         if (node > 0) v = __fadd_rn(v, __fmul_rn(a.alpha, __ldcg(z + (long long)node * a.dim + j)));   // L2 loads: the table is written by other SMs
         return v;
     }
-    const int b = (a.tree == PMP_TREE_BINARY) ? 2 : a.b;
-    long long s = 1;
-    for (int l = 0; l < a.depth; ++l) {
-        long long digit = (node / s) % b;
-        if (digit != 0) { long long anc = node % (s * b); v = __fadd_rn(v, __fmul_rn(a.alpha, __ldcg(z + anc * a.dim + j))); }
-        s *= b;
-    }
+    for_each_ancestor(a.tree, a.b, a.depth, node, [&](int anc) { v = __fadd_rn(v, __fmul_rn(a.alpha, __ldcg(z + (long long)anc * a.dim + j))); });
     return v;
 }
 

@@ -52,16 +52,44 @@ struct LeanRegs {
     int next; float n0, n1, n2;
 };
 
+// ---- flag-in-data hand-offs of the persistent chain kernels ------------------------------------------------------------------------
+// Everything that crosses between the sweep CTAs and the acceptance CTA inside an iteration travels as 8-byte words
+// {32-bit payload | tag << 32}: an 8-byte access is single-copy atomic, so a word whose tag is current is complete by itself — no
+// fence, no counter, no second L2 round trip (the scheme of the cross-GPU exchange in chain_persistent_multi.cuh, and of NCCL's LL
+// protocol).  tag of iteration `it` of a launch = epoch + it + 1, epoch = iterations of all earlier launches on this context (never
+// reused, so nothing is ever reset and a stale word can never look current).
+// (The other direction — the sweep CTAs' partial sums — stays an L2-side reduction: integer RED.64 per node, fence, arrival counter.  A
+//  slot-per-CTA tagged variant was built and measured: the acceptance SM has to pull ~18 slots x 16 B x 1024 nodes through its own L2
+//  port every poll round, 28.3 us per iteration against 19.8.)
+//   nodes  next iteration's nodes {b0 | tag}, {b1 | tag}, {sigma | tag} at [node][4]; the sweep CTAs poll their tile's nodes
+//   zt     next iteration's standard normals {float | tag} at [2][3P] (half by Philox iteration parity), written by the sweep CTAs'
+//          side job, read by the acceptance CTA
+// One buffer of nodes suffices: the nodes of it + 1 are written after every sweep CTA has arrived for it, i.e. after it has read the
+// nodes of it.  Two halves of normals: a sweep CTA writes the normals of it + 1 (half (it + 1) & 1) at the start of its sweep it, which it
+// can only enter after the acceptance of it - 1 — the reader of the other half — has published its nodes.
+struct Handoff {
+    unsigned long long* nodes;
+    unsigned long long* zt;
+    unsigned int epoch;
+};
+__host__ __device__ inline size_t handoff_node_words(int P) { return (size_t)P * 4; }
+__host__ __device__ inline size_t handoff_z_words(int P) { return (size_t)2 * 3 * P; }
+
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu_v2(unsigned long long* p, unsigned long long a, unsigned long long b) { asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void ld_relaxed_gpu_v2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory"); }
+__device__ __forceinline__ bool hs_tag_ok(unsigned long long w, unsigned long long tag) { return (w & 0xffffffff00000000ull) == tag; }
+// a hand-off that never arrives is a protocol bug (or a dead peer CTA): trap instead of hanging the GPU
+struct SpinGuard {
+    unsigned spins = 0; unsigned long long t0 = 0;
+    __device__ __forceinline__ void tick() { if ((++spins & 4095u) == 0) { const unsigned long long t = globaltimer_ns(); if (t0 == 0) t0 = t; else if (t - t0 > 20000000000ull) __trap(); } }
+};
+
 // proposal_value_z (accept.cuh) with the normals in shared memory
 __device__ __forceinline__ float proposal_value_zs(const ProposeArgs& a, const float* z, int node, int j, float v) {
     if (a.tree == PMP_TREE_FLAT) { if (node > 0) v = __fadd_rn(v, __fmul_rn(a.alpha, z[node * a.dim + j])); return v; }
-    const int b = (a.tree == PMP_TREE_BINARY) ? 2 : a.b;
-    long long s = 1;
-    for (int l = 0; l < a.depth; ++l) {
-        long long digit = (node / s) % b;
-        if (digit != 0) { long long anc = node % (s * b); v = __fadd_rn(v, __fmul_rn(a.alpha, z[anc * a.dim + j])); }
-        s *= b;
-    }
+    for_each_ancestor(a.tree, a.b, a.depth, node, [&](int anc) { v = __fadd_rn(v, __fmul_rn(a.alpha, z[anc * a.dim + j])); });
     return v;
 }
 
@@ -140,8 +168,11 @@ __device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSme
     PMP_STAMP(dbg, 1);
 }
 
+// qin: the per-node sums are already in registers.  hs (persistent kernels with flag-in-data hand-offs): the next iteration's normals come from the tagged table hs->zt and the next nodes
+// are ALSO published as tagged words in hs->nodes; `tag` is this iteration's, `tag + 2^32` the next one's.
 template <int ALGO>
-__device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], const int* s_pick, int z_mode) {
+__device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], const int* s_pick, int z_mode,
+                                          const unsigned long long* qin = nullptr, const Handoff* hs = nullptr, unsigned long long tag = 0) {
     const AcceptArgs& a = fa.base;
     const pmp_config& cfg = a.cfg;
     const int P = a.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -154,8 +185,18 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
     // ---- log-targets from the integer sums (one L2 round trip), log-weights, maximum ------------------------------------
     unsigned long long q[LEAN_K];
 #pragma unroll
-    for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? __ldcg(a.acc + p) : 0ull; }
-    if (z_mode == LEAN_Z_TABLE_CRIT && fa.make_next) {       // same L2 round trip as the sums; first read after the block barriers below
+    for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? (qin ? qin[k] : __ldcg(a.acc + p)) : 0ull; }
+    if (hs && fa.make_next) {                                 // tagged normals: written by the sweep CTAs' side job at the start of their sweep — long since there
+        const unsigned long long* zn = hs->zt + ((r.iter + 1) & 1) * (long long)(P * 3);
+        unsigned long long zw[3 * LEAN_K];
+#pragma unroll
+        for (int k = 0; k < 3 * LEAN_K; ++k) { const int g = tid + k * ACCEPT_THREADS; zw[k] = (g < 3 * P) ? ld_relaxed_gpu_u64(zn + g) : tag; }
+#pragma unroll
+        for (int k = 0; k < 3 * LEAN_K; ++k) {
+            const int g = tid + k * ACCEPT_THREADS;
+            if (g < 3 * P) { SpinGuard sg; while (!hs_tag_ok(zw[k], tag)) { sg.tick(); zw[k] = ld_relaxed_gpu_u64(zn + g); } s.z[g] = __uint_as_float((unsigned)zw[k]); }
+        }
+    } else if (z_mode == LEAN_Z_TABLE_CRIT && fa.make_next) {       // same L2 round trip as the sums; first read after the block barriers below
         const float* zn = fa.z + ((r.iter + 1) & 1) * (long long)(P * 3);
         float zr[3 * LEAN_K];
 #pragma unroll
@@ -168,7 +209,7 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
     for (int k = 0; k < LEAN_K; ++k) {
         const int p = tid + k * ACCEPT_THREADS;
         if (p < P) {
-            a.acc[p] = 0ull;
+            if (!qin) a.acc[p] = 0ull;
             const double S = (double)(long long)q[k] * (1.0 / (double)(1 << FX_SHIFT));
             double v = (s.c1[p] - 0.5 * S) * a.inv_scale;
             if ((double)(long long)q[k] >= a.sat_limit || !(v == v)) v = -INFINITY;
@@ -258,9 +299,12 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
     if (a.advance) {
         if (fa.make_next) {
             float* props_out = const_cast<float*>(a.props);
+            const unsigned long long tag_next = tag + (1ull << 32);
             for (int g = tid; g < P * 3; g += ACCEPT_THREADS) {
                 const int node = g / 3, j = g - 3 * node;
-                props_out[g] = proposal_value_zs(fa.gen, s.z, node, j, j == 0 ? r.n0 : (j == 1 ? r.n1 : r.n2));
+                const float v = proposal_value_zs(fa.gen, s.z, node, j, j == 0 ? r.n0 : (j == 1 ? r.n1 : r.n2));
+                if (hs) st_relaxed_gpu_u64(hs->nodes + 4 * node + j, (unsigned long long)__float_as_uint(v) | tag_next);   // what the sweep CTAs poll
+                props_out[g] = v;
             }
         }
         if (tid == 0) a.cnt->iteration = r.iter + 1;

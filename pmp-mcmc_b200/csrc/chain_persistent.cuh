@@ -33,7 +33,20 @@ struct PersistArgs {
     PersistSync* sync;
     int iters;
     int max_chunks;          // chunks per sweep CTA that fit the dynamic shared memory
+    Handoff hs;              // HS kernels: flag-in-data hand-offs (accept_lean.cuh)
 };
+
+// A sweep CTA's thread i < PERSIST_PT fetches node (node_base + i) of iteration `it`: plain memory for the first iteration of a launch
+// (written by propose_kernel before the launch), the tagged words the acceptance CTA publishes afterwards.
+__device__ __forceinline__ void fetch_node(const Handoff& hs, const float* theta, int node, int P, bool first, unsigned long long tag, float& b0, float& b1, float& sg_) {
+    if (node >= P) { b0 = 0.f; b1 = 0.f; sg_ = 0.f; return; }
+    if (first) { b0 = __ldcg(theta + 3ll * node); b1 = __ldcg(theta + 3ll * node + 1); sg_ = __ldcg(theta + 3ll * node + 2); return; }
+    const unsigned long long* w = hs.nodes + 4ll * node;
+    unsigned long long w0, w1, w2;
+    SpinGuard sg;
+    for (;;) { ld_relaxed_gpu_v2(w, w0, w1); w2 = ld_relaxed_gpu_u64(w + 2); if (hs_tag_ok(w0, tag) && hs_tag_ok(w1, tag) && hs_tag_ok(w2, tag)) break; sg.tick(); }
+    b0 = __uint_as_float((unsigned)w0); b1 = __uint_as_float((unsigned)w1); sg_ = __uint_as_float((unsigned)w2);
+}
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -42,7 +55,7 @@ __device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target
     while ((int)(ld_acquire(p) - target) < 0) { if (++spins > 400000000u) __trap(); }
 }
 
-template <int ALGO>
+template <int ALGO, bool HS>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(const __grid_constant__ PersistArgs pa) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int tid = threadIdx.x;
@@ -59,13 +72,18 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 8] = clock64(); pa.fa.base.dbg[32 + 24] = globaltimer_ns(); }
             if (tid == 0) spin_until_ge(&pa.sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
             __syncthreads();
-            lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release(&pa.sync->version, (unsigned)(it + 1));
+            if (HS) {       // the next nodes and normals travel as tagged words: no fence, no version counter
+                lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT, nullptr, &pa.hs, (unsigned long long)(pa.hs.epoch + (unsigned)it + 1u) << 32);
+                __syncthreads();
+            } else {
+                lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) st_release(&pa.sync->version, (unsigned)(it + 1));
+            }
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 9] = clock64(); pa.fa.base.dbg[32 + 25] = globaltimer_ns(); }
             lean_post<ALGO>(pa.fa, ls, lr);
-            __threadfence();          // trace cursor and state are read back by the next pre / by the host
+            __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre / by the host
             __syncthreads();
         }
         return;
@@ -112,24 +130,44 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     for (int it = 0; it < pa.iters; ++it) {
         unsigned long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
         PMP_STAMP(dbg, 0);
-        if (tid == 0 && it > 0) spin_until_ge(&pa.sync->version, (unsigned)it);
-        __syncthreads();
+        const unsigned long long tag = (unsigned long long)(pa.hs.epoch + (unsigned)it + 1u) << 32;      // HS: tag of this iteration's nodes, sums and normals
+        if (!HS) {
+            if (tid == 0 && it > 0) spin_until_ge(&pa.sync->version, (unsigned)it);
+            __syncthreads();
+        }
         PMP_STAMP(dbg, 1);
         {   // side job: this CTA's slice of the NEXT iteration's normals (they depend on counters only); read by the acceptance CTA
             const int zcount = a.P * 3, per = (zcount + n_sweep - 1) / n_sweep;
             const unsigned long long iter = iter0 + (unsigned long long)it;
             for (int k = PERSIST_THREADS - 1 - tid; k < per; k += PERSIST_THREADS) {
                 const int e = blockIdx.x * per + k;
-                if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+                if (e < zcount) {
+                    const float zv = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+                    if (HS) st_relaxed_gpu_u64(pa.hs.zt + ((iter + 1) & 1) * (long long)zcount + e, (unsigned long long)__float_as_uint(zv) | tag);
+                    else a.z[((iter + 1) & 1) * (long long)zcount + e] = zv;
+                }
             }
+        }
+        if (HS && nseg == 0 && it > 0) {      // a CTA without units must not run ahead of the chain (its normals would overwrite a half still in use)
+            if (tid == 0) { float t0, t1, t2; fetch_node(pa.hs, a.theta, 0, a.P, false, tag, t0, t1, t2); }
+            __syncthreads();
         }
         for (int s = 0; s < nseg; ++s) {
             const int node_base = seg_tile[s] * PT;
-            for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {
-                int node = node_base + i / 3, j = i - (i / 3) * 3;
-                float v = (node < a.P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
-                sprops[i] = v;
-                if (j == 2) sscl[i / 3] = (node < a.P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+            if (HS) {
+                if (tid < PT) {
+                    float v0, v1, v2;
+                    fetch_node(pa.hs, a.theta, node_base + tid, a.P, it == 0, tag, v0, v1, v2);
+                    sprops[3 * tid] = v0; sprops[3 * tid + 1] = v1; sprops[3 * tid + 2] = v2;
+                    sscl[tid] = (node_base + tid < a.P) ? (double)(1 << FX_SHIFT) / ((double)v2 * (double)v2) : 0.0;
+                }
+            } else {
+                for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {
+                    int node = node_base + i / 3, j = i - (i / 3) * 3;
+                    float v = (node < a.P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
+                    sprops[i] = v;
+                    if (j == 2) sscl[i / 3] = (node < a.P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+                }
             }
             __syncthreads();
             if (s == 0) PMP_STAMP(dbg, 2);

@@ -47,15 +47,16 @@ __device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long* p, u
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
-// Executed by the whole acceptance CTA once the local sweep CTAs have arrived: acc[p] := sum over ranks of their acc[p].
-__device__ __forceinline__ void peer_allreduce_acc(const PeerXchg& x, unsigned long long* acc, int P, int it) {
+// Executed by the whole acceptance CTA once the local sweep CTAs' sums are in: q[k] (this rank's sum of node tid + k * ACCEPT_THREADS)
+// := sum over ranks.  acc != nullptr (counter-based hand-off): the local sums are read from / the totals written back to acc.
+__device__ __forceinline__ void peer_allreduce_acc(const PeerXchg& x, unsigned long long* acc, int P, int it, unsigned long long* qreg = nullptr) {
     const int tid = threadIdx.x;
     const unsigned long long e = x.base + (unsigned long long)it;
     const unsigned long long tag = ((e + 1ull) & 0xffffffffull) << 32;
     const size_t slot = (size_t)(e & 1ull) * PEER_MAX_WORLD * MAX_NODES * 2;
     unsigned long long q[LEAN_K];
 #pragma unroll
-    for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? __ldcg(acc + p) : 0ull; }
+    for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? (qreg ? qreg[k] : __ldcg(acc + p)) : 0ull; }
     for (int r = 0; r < x.world; ++r) {
         if (r == x.me) continue;
         unsigned long long* dst = x.peer[r] + slot + (size_t)x.me * MAX_NODES * 2;
@@ -83,7 +84,7 @@ __device__ __forceinline__ void peer_allreduce_acc(const PeerXchg& x, unsigned l
                 }
                 sum += (lo & 0xffffffffull) | (hi << 32);
             }
-            acc[p] = sum;       // read back by the same thread in lean_crit
+            if (qreg) qreg[k] = sum; else acc[p] = sum;       // read back by the same thread in lean_crit
         }
     }
 }
@@ -93,6 +94,7 @@ struct PersistChain {
     AcceptFastArgs fa;
     PersistSync* sync;
     PeerXchg xchg;             // world == 1: unused
+    Handoff hs;                // HS kernels: this chain's flag-in-data hand-off buffers (accept_lean.cuh)
 };
 
 struct PersistMultiArgs {
@@ -113,7 +115,7 @@ __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %
 // between sweeps.  NG = 4 when at least four chains are resident: on a shard of the data (world_size > 1) the sweep itself is
 // short and the per-iteration round trips dominate, so more of them must be in flight.  The per-node sums are integers, so
 // splitting the chunk lanes NG ways changes no bit of the result.
-template <int ALGO, int NG>
+template <int ALGO, int NG, bool HS>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_kernel(const __grid_constant__ PersistMultiArgs pa) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int tid = threadIdx.x;
@@ -134,12 +136,18 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 if (tid == 0) spin_until_ge(&pa.ch[c].sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
                 __syncthreads();
                 if (pa.ch[c].xchg.world > 1) peer_allreduce_acc(pa.ch[c].xchg, fa.base.acc, fa.base.P, it);
-                lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
-                __threadfence();
-                __syncthreads();
-                if (tid == 0) st_release(&pa.ch[c].sync->version, (unsigned)(it + 1));
+                if (HS) {
+                    const Handoff& hs = pa.ch[c].hs;
+                    lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT, nullptr, &hs, (unsigned long long)(hs.epoch + (unsigned)it + 1u) << 32);
+                    __syncthreads();
+                } else {
+                    lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) st_release(&pa.ch[c].sync->version, (unsigned)(it + 1));
+                }
                 lean_post<ALGO>(fa, ls, lr);
-                __threadfence();          // trace cursor and state are read back by the next pre of this chain / by the host
+                __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre of this chain / by the host
                 __syncthreads();
             }
         }
@@ -196,24 +204,45 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
 #pragma unroll 1
         for (int c = half; c < K; c += NG) {                     // this group's chains: group, group + NG, ...
             const SweepArgs& a = pa.ch[c].sw;
-            if (htid == 0 && it > 0) spin_until_ge(&pa.ch[c].sync->version, (unsigned)it);
-            group_sync<NG>(half);
+            const Handoff& hs = pa.ch[c].hs;
+            const unsigned long long tag = (unsigned long long)(hs.epoch + (unsigned)it + 1u) << 32;
+            if (!HS) {
+                if (htid == 0 && it > 0) spin_until_ge(&pa.ch[c].sync->version, (unsigned)it);
+                group_sync<NG>(half);
+            }
             {   // side job: this CTA's slice of the chain's NEXT-iteration normals (they depend on counters only)
                 const int zcount = P * 3, per = (zcount + n_sweep - 1) / n_sweep;
                 const unsigned long long iter = s_iter0[c] + (unsigned long long)it;
                 for (int k = HT - 1 - htid; k < per; k += HT) {
                     const int e = blockIdx.x * per + k;
-                    if (e < zcount) a.z[((iter + 1) & 1) * (long long)zcount + e] = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+                    if (e < zcount) {
+                        const float zv = (float)stream_step(a.gen.seed, iter + 1, (unsigned long long)e, a.gen.uniform);
+                        if (HS) st_relaxed_gpu_u64(hs.zt + ((iter + 1) & 1) * (long long)zcount + e, (unsigned long long)__float_as_uint(zv) | tag);
+                        else a.z[((iter + 1) & 1) * (long long)zcount + e] = zv;
+                    }
                 }
+            }
+            if (HS && nseg == 0 && it > 0) {      // a CTA without units must not run ahead of the chain
+                if (htid == 0) { float t0, t1, t2; fetch_node(hs, a.theta, 0, P, false, tag, t0, t1, t2); }
+                group_sync<NG>(half);
             }
             bool sat = false;
             for (int s = 0; s < nseg; ++s) {
                 const int node_base = seg_tile[s] * PT;
-                for (int i = htid; i < PT * 3; i += HT) {
-                    int node = node_base + i / 3, j = i - (i / 3) * 3;
-                    float v = (node < P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
-                    sprops[i] = v;
-                    if (j == 2) sscl[i / 3] = (node < P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+                if (HS) {
+                    for (int i = htid; i < PT; i += HT) {
+                        float v0, v1, v2;
+                        fetch_node(hs, a.theta, node_base + i, P, it == 0, tag, v0, v1, v2);
+                        sprops[3 * i] = v0; sprops[3 * i + 1] = v1; sprops[3 * i + 2] = v2;
+                        sscl[i] = (node_base + i < P) ? (double)(1 << FX_SHIFT) / ((double)v2 * (double)v2) : 0.0;
+                    }
+                } else {
+                    for (int i = htid; i < PT * 3; i += HT) {
+                        int node = node_base + i / 3, j = i - (i / 3) * 3;
+                        float v = (node < P) ? __ldcg(a.theta + (long long)node * 3 + j) : 0.f;
+                        sprops[i] = v;
+                        if (j == 2) sscl[i / 3] = (node < P) ? (double)(1 << FX_SHIFT) / ((double)v * (double)v) : 0.0;
+                    }
                 }
                 group_sync<NG>(half);
                 float b0[R], b1[R]; double scl[R]; unsigned long long accq[R];

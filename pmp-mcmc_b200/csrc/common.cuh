@@ -89,10 +89,14 @@ struct pmp_ctx {
     float* d_z = nullptr;              // [2, P*dim] prefetched standard normals (current / next iteration)
     unsigned long long* d_dbg = nullptr; // optional phase stamps
     void* d_psync = nullptr;           // PersistSync of the cooperative chain kernel
+    unsigned long long* d_hs = nullptr; // flag-in-data hand-off buffers of the persistent chain kernels: sums | nodes | normals (accept_lean.cuh)
+    size_t hs_words = 0; int hs_grid = 0, hs_P = 0;
+    unsigned int hs_epoch = 0;         // iterations of all earlier hand-off launches on this ctx (tags are never reused)
     unsigned int* d_done = nullptr;    // CTA completion counter of the fused sweep+accept kernel
     unsigned long long host_iter = 0;  // host mirror of d_cnt->iteration
     long long z_valid_iter = -1;       // iteration whose normals are in d_z, -1: none
     bool lt_valid = false;             // d_lt holds the log-targets of the current proposals
+    bool props_external = false;       // d_props were written by the caller (pmp_write_proposals), not generated about d_state by pmp_propose
     bool acc_pending = false;          // d_acc holds an un-finalised sweep
 
     pmp::TraceBuffers trace;

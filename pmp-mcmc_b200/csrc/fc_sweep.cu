@@ -33,6 +33,7 @@
 //     TMEM), followed by the log-softmax/NLL and the fixed-point row sum: one kernel and one activation round trip less.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -293,6 +294,9 @@ struct Gemm2Args {
     int glm_kind;
     unsigned long long* glm_acc;   // [n_total] fixed-point sums
     double glm_sat;           // per-partial saturation bound in fixed-point units
+    // RELU_SPLIT, base pass of the delta formulation (node 0 only): also keep the PRE-activations acc + bias, row-major [rows, n_total]
+    __half* t_out16;          // binary16: enough to locate the ReLU kinks (layers 1, 2)
+    float* t_out32;           // float32: layer 3 (its activations feed the float32 last layer)
 };
 
 template <int BN, int EPI, int NSTAGE>
@@ -423,20 +427,42 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint32_t hp[16], lp[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float a0 = fmaxf(__uint_as_float(v[2 * i]) + __ldg(bias + cc * 32 + 2 * i), 0.f);
-                        float a1 = fmaxf(__uint_as_float(v[2 * i + 1]) + __ldg(bias + cc * 32 + 2 * i + 1), 0.f);
+                        const float t0 = __uint_as_float(v[2 * i]) + __ldg(bias + cc * 32 + 2 * i);
+                        const float t1 = __uint_as_float(v[2 * i + 1]) + __ldg(bias + cc * 32 + 2 * i + 1);
+                        v[2 * i] = __float_as_uint(t0); v[2 * i + 1] = __float_as_uint(t1);       // pre-activations, kept for t_out16 / t_out32
+                        const float a0 = fmaxf(t0, 0.f), a1 = fmaxf(t1, 0.f);
                         __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
                         __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
                         hp[i] = pack_bf16x2(h0, h1); lp[i] = pack_bf16x2(l0, l1);
                     }
                     if (row < g.M) {
                         const int col = col0 + cc * 32, kt = col >> 6, cin = col & 63;
-                        uint4* d0 = reinterpret_cast<uint4*>(oblk + (long long)kt * (128 * 64) + cin);
-                        uint4* d1 = reinterpret_cast<uint4*>(oblk + (long long)(kt_half + kt) * (128 * 64) + cin);
+                        if (g.out) {
+                            uint4* d0 = reinterpret_cast<uint4*>(oblk + (long long)kt * (128 * 64) + cin);
+                            uint4* d1 = reinterpret_cast<uint4*>(oblk + (long long)(kt_half + kt) * (128 * 64) + cin);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            d0[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-                            d1[q] = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+                            for (int q = 0; q < 4; ++q) {
+                                d0[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+                                d1[q] = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+                            }
+                        }
+                        if (g.t_out16) {
+                            uint4* dt = reinterpret_cast<uint4*>(g.t_out16 + (long long)row * g.n_total + col);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const __half2 hh = __floats2half2_rn(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]));
+                                    w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                                }
+                                dt[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        }
+                        if (g.t_out32) {
+                            uint4* dt = reinterpret_cast<uint4*>(g.t_out32 + (long long)row * g.n_total + col);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) dt[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                         }
                     }
                 }
@@ -544,6 +570,284 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
+
+// ===================================================== v3: delta formulation ================================================
+// All P nodes of an iteration are the current state (node 0) plus small increments: |dW| ~ alpha sqrt(depth) = 1e-4 .. 3e-4 against
+// |W| ~ 3e-2.  With t^l_p the pre-activations of layer l for node p and a^l_p = relu(t^l_p):
+//     t^1_p - t^1_0 = X . dW1_p + db1_p
+//     t^l_p - t^l_0 = da^(l-1)_p . W^l_p + a^(l-1)_0 . dW^l_p + db^l_p          (exact identity; da = a_p - a_0, dW = W_p - W_0)
+//     da^l_p        = relu(t^l_0 + (t^l_p - t^l_0)) - relu(t^l_0)
+// Every product on the right has one SMALL factor, so ONE bf16 x bf16 product (fp32 accumulation) carries it to 2^-9 of a small term
+// — the accuracy the 3-product split reaches on the full-size term — and node 0's own pre-activations t^l_0 come from one "base pass"
+// per iteration with the split (fc_gemm2_kernel).  Hardware flops per node: 1x (layer 1) + 2x (layers 2, 3: K doubles, [da | a_0] .
+// [W_p ; dW_p]) of the algorithmic count instead of 3x.  t^l_0 is only needed to locate ReLU kinks (binary16 suffices: the error is
+// 2^-11 |t_0| and matters only where |t_0| <~ |delta|) except in the last hidden layer, where a^3_p = relu(t^3_0 + delta) feeds the
+// float32 128 -> 10 layer + log-softmax + NLL in the epilogue exactly as in fc_gemm2_kernel (t^3_0 kept in float32).
+// Same skeleton as fc_gemm2_kernel: CTA pairs (cta_group::2), persistent, node-fastest tile order, two TMEM accumulator stages.
+enum { EPI3_DELTA_RELU = 0, EPI3_L4_NLL = 1 };
+constexpr int L4_NB = 8;                                          // nodes per launch whose last layer fits the L4_NLL kernel's shared memory
+__device__ __forceinline__ float2 ffma2f(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+struct Gemm3Args {
+    int M, nb, n_total, mb128;
+    int nk_a, nk_total;       // k-blocks (64 wide) taken from the per-node A source, and in total (the rest come from the shared node-0 source)
+    int a_rowmajor;           // 1: A is the row-major data matrix (3-D map, the same for every node: layer 1); 0: tile-major 5-D maps
+    const float* dbias;       // [nb, dbias_stride], already offset to this layer: b_p - b_0
+    int dbias_stride;
+    const __half* t0h;        // DELTA_RELU: node 0's pre-activations [rows, n_total]
+    __nv_bfloat16* out;       // DELTA_RELU: da, tile-major [nb][mb128][n_total/64][128][64]
+    const float* t0f;         // L4_NLL: node 0's layer-3 pre-activations [rows, 128]
+    const float* theta;       // L4_NLL: node parameters (float32, torch order) of the first node of the batch
+    long long theta_stride;
+    const int* labels;
+    unsigned long long* loss; // [nb] fixed-point sums
+};
+
+template <int BN, int EPI, int NSTAGE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
+fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB, const Gemm3Args g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int BH = BN / 2;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BH * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = 2 * BN;
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+    // L4_NLL: the last layer (transposed, 12-float rows), the layer-3 bias increments and the last bias of ALL nodes of the batch, loaded once
+    float* s_w4_all = reinterpret_cast<float*>(smem + (size_t)NSTAGE * STAGE_BYTES);           // [L4_NB][H3 * 12]
+    float* s_b3_all = s_w4_all + L4_NB * H3 * 12;                                              // [L4_NB][H3]
+    float* s_b4_all = s_b3_all + L4_NB * H3;                                                   // [L4_NB][NCLS_PAD]
+    __shared__ float s_z[EPI == EPI3_L4_NLL ? BM * (NCLS + 1) : 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int nblk_n = g.n_total / BN;
+    const int inner = nblk_n * g.nb;
+    const int total = ((g.M + 2 * BM - 1) / (2 * BM)) * inner;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int num_k = g.nk_total;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * GEMM2_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                         // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0;
+            for (int t = pair; t < total; t += npairs) {
+                const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
+                const int row0 = m_blk * 2 * BM + (int)rank * BM, col0 = n_blk * BN + (int)rank * BH;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, round = it / NSTAGE;
+                    if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                    if (g.a_rowmajor) tma_load_3d_2sm(st, &tmA, lbar, kb * BK, row0, 0);
+                    else if (kb < g.nk_a) tma_load_5d_2sm(st, &tmA, lbar, 0, 0, kb, m_blk * 2 + (int)rank, batch);
+                    else tma_load_5d_2sm(st, &tmA0, lbar, 0, 0, kb - g.nk_a, m_blk * 2 + (int)rank, 0);
+                    tma_load_3d_2sm(st + A_BYTES, &tmB, lbar, kb * BK, col0, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {                            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            uint32_t it = 0; int j = 0;
+            for (int t = pair; t < total; t += npairs, ++j) {
+                const int acc = j & 1, use = j >> 1;
+                if (use > 0) { mbar_wait(&tempty_bar[acc], (use - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, round = it / NSTAGE;
+                    mbar_wait(&full_bar[s], round & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    const uint64_t da = umma_desc_sw128(st), db = umma_desc_sw128(st + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2sm(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty_bar[s]);
+                }
+                umma_commit_2sm(&tfull_bar[acc]);
+            }
+        }
+    } else {                                                     // ===== epilogue warps 2..9 (both CTAs) =====
+        const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int et = (warp - 2) * 32 + lane;
+        constexpr int CH = BN / 2;
+        const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+        if (EPI == EPI3_L4_NLL) {                                // once per launch: every node's 128 -> 10 layer into shared memory
+            for (int b = 0; b < g.nb; ++b) {
+                const float* th = g.theta + (long long)b * g.theta_stride;
+                for (int i = et; i < NCLS * H3; i += 32 * GEMM2_EPI_WARPS) { const int c = i / H3, jj = i - c * H3; s_w4_all[b * (H3 * 12) + jj * 12 + c] = __ldg(th + OFF_W4 + i); }
+                if (et < H3) { s_w4_all[b * (H3 * 12) + et * 12 + 10] = 0.f; s_w4_all[b * (H3 * 12) + et * 12 + 11] = 0.f; s_b3_all[b * H3 + et] = __ldg(g.dbias + (long long)b * g.dbias_stride + et); }
+                if (et < NCLS_PAD) s_b4_all[b * NCLS_PAD + et] = et < NCLS ? __ldg(th + OFF_B4 + et) : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        int j = 0;
+        for (int t = pair; t < total; t += npairs, ++j) {
+            const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
+            const int acc = j & 1, use = j >> 1;
+            const int lrow = quarter * 32 + lane;
+            const int row = m_blk * 2 * BM + (int)rank * BM + lrow;
+            const bool valid = row < g.M;
+            const float* s_w4 = s_w4_all + batch * (H3 * 12);
+            const float* s_b3 = s_b3_all + batch * H3;
+            const float* s_b4 = s_b4_all + batch * NCLS_PAD;
+            mbar_wait(&tfull_bar[acc], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * CH);
+            if (EPI == EPI3_DELTA_RELU) {
+                const int col0 = n_blk * BN + chalf * CH;
+                const float* db = g.dbias + (long long)batch * g.dbias_stride + col0;
+                const int kts = g.n_total / 64;
+                const long long blk = (long long)batch * g.mb128 + (m_blk * 2 + (int)rank);
+                __nv_bfloat16* oblk = g.out + blk * (long long)kts * (128 * 64) + (long long)lrow * 64;
+                const __half* trow = g.t0h + (long long)(valid ? row : 0) * g.n_total + col0;
+#pragma unroll 1
+                for (int cc = 0; cc < CH / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+                    uint4 tq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tq[q] = __ldg(reinterpret_cast<const uint4*>(trow + cc * 32) + q);
+                    const __half2* th2 = reinterpret_cast<const __half2*>(tq);
+                    uint32_t dp[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 t0 = __half22float2(th2[i]);
+                        const float d0 = __uint_as_float(v[2 * i]) + __ldg(db + cc * 32 + 2 * i), d1 = __uint_as_float(v[2 * i + 1]) + __ldg(db + cc * 32 + 2 * i + 1);
+                        const float s0 = t0.x + d0, s1 = t0.y + d1;
+                        // relu(t0 + d) - relu(t0), without cancellation where both sides are active
+                        const float a0 = t0.x > 0.f ? (s0 > 0.f ? d0 : -t0.x) : fmaxf(s0, 0.f);
+                        const float a1 = t0.y > 0.f ? (s1 > 0.f ? d1 : -t0.y) : fmaxf(s1, 0.f);
+                        dp[i] = pack_bf16x2(__float2bfloat16_rn(a0), __float2bfloat16_rn(a1));
+                    }
+                    if (valid) {
+                        const int col = col0 + cc * 32, kt = col >> 6, cin = col & 63;
+                        uint4* d = reinterpret_cast<uint4*>(oblk + (long long)kt * (128 * 64) + cin);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) d[q] = make_uint4(dp[4 * q], dp[4 * q + 1], dp[4 * q + 2], dp[4 * q + 3]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);
+            } else {
+                float2 z2[NCLS / 2];
+#pragma unroll
+                for (int c = 0; c < NCLS / 2; ++c) z2[c] = chalf == 0 ? make_float2(s_b4[2 * c], s_b4[2 * c + 1]) : make_float2(0.f, 0.f);
+                const float* trow = g.t0f + (long long)(valid ? row : 0) * H3 + chalf * CH;
+#pragma unroll 1
+                for (int cc = 0; cc < CH / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+                    float4 tq[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tq[q] = __ldg(reinterpret_cast<const float4*>(trow + cc * 32) + q);
+                    const float* t0 = reinterpret_cast<const float*>(tq);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int jj = chalf * CH + cc * 32 + i;
+                        const float a = fmaxf(t0[i] + (__uint_as_float(v[i]) + s_b3[jj]), 0.f);
+                        const float4 w0 = *reinterpret_cast<const float4*>(&s_w4[jj * 12]);
+                        const float4 w1 = *reinterpret_cast<const float4*>(&s_w4[jj * 12 + 4]);
+                        const float2 w2 = *reinterpret_cast<const float2*>(&s_w4[jj * 12 + 8]);
+                        const float2 aa = make_float2(a, a);          // packed FMA: two logits per instruction, the same per-logit rounding sequence as scalar fmaf
+                        z2[0] = ffma2f(aa, make_float2(w0.x, w0.y), z2[0]); z2[1] = ffma2f(aa, make_float2(w0.z, w0.w), z2[1]);
+                        z2[2] = ffma2f(aa, make_float2(w1.x, w1.y), z2[2]); z2[3] = ffma2f(aa, make_float2(w1.z, w1.w), z2[3]);
+                        z2[4] = ffma2f(aa, w2, z2[4]);
+                    }
+                }
+                float z[NCLS];
+#pragma unroll
+                for (int c = 0; c < NCLS / 2; ++c) { z[2 * c] = z2[c].x; z[2 * c + 1] = z2[c].y; }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);
+                if (chalf == 1) {
+#pragma unroll
+                    for (int c = 0; c < NCLS; ++c) s_z[lrow * (NCLS + 1) + c] = z[c];
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (chalf == 0) {
+#pragma unroll
+                    for (int c = 0; c < NCLS; ++c) z[c] += s_z[lrow * (NCLS + 1) + c];
+                    float mx = z[0];
+#pragma unroll
+                    for (int c = 1; c < NCLS; ++c) mx = fmaxf(mx, z[c]);
+                    float se = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCLS; ++c) se += expf(z[c] - mx);
+                    float nll = 0.f;
+                    if (valid) {
+                        const int lab = g.labels[row];
+                        float zl = z[0];
+#pragma unroll
+                        for (int c = 1; c < NCLS; ++c) zl = (lab == c) ? z[c] : zl;
+                        nll = (mx + logf(se)) - zl;
+                    }
+                    long long q = valid ? __double2ll_rn((double)nll * 4294967296.0) : 0ll;
+                    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                    if (lane == 0 && q != 0) atomicAdd(g.loss + batch, (unsigned long long)q);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+// delta operands of one batch of nodes (theta_0 = node 0 of the iteration):
+//   cat = 0:  out [nb, rows, Kpad]   = bf16(W_p - W_0)                       (layer 1)
+//   cat = 1:  out [nb, rows, 2 Kpad] = [ bf16(W_p) | bf16(W_p - W_0) ]        (layers 2, 3: K-concatenated with [da | a_0])
+__global__ void delta_w_kernel(const float* __restrict__ theta, const float* __restrict__ theta0, long long theta_stride, long long w_off, int rows, int K, int Kpad,
+                               int cat, __nv_bfloat16* __restrict__ out, int nb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long per = (long long)rows * Kpad;
+    if (i >= per * nb) return;
+    int b = (int)(i / per); long long rem = i - b * per;
+    int r = (int)(rem / Kpad), c = (int)(rem - (long long)r * Kpad);
+    float w = 0.f, d = 0.f;
+    if (c < K) { w = theta[b * theta_stride + w_off + (long long)r * K + c]; d = w - theta0[w_off + (long long)r * K + c]; }
+    if (cat) { __nv_bfloat16* o = out + ((long long)b * rows + r) * (2ll * Kpad); o[c] = __float2bfloat16_rn(w); o[Kpad + c] = __float2bfloat16_rn(d); }
+    else out[((long long)b * rows + r) * Kpad + c] = __float2bfloat16_rn(d);
+}
+__global__ void delta_bias_kernel(const float* __restrict__ theta, const float* __restrict__ theta0, long long theta_stride, float* __restrict__ out, int nb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = H1 + H2 + H3 + NCLS_PAD;
+    if (i >= per * nb) return;
+    int b = i / per, c = i - b * per;
+    const float* t = theta + b * theta_stride;
+    float v = 0.f;
+    if (c < H1) v = t[OFF_B1 + c] - theta0[OFF_B1 + c];
+    else if (c < H1 + H2) v = t[OFF_B2 + c - H1] - theta0[OFF_B2 + c - H1];
+    else if (c < H1 + H2 + H3) v = t[OFF_B3 + c - H1 - H2] - theta0[OFF_B3 + c - H1 - H2];
+    out[i] = v;
+}
+
 // v f32 [rows, K] (node-strided) -> bf16 [nb, rows_pad, 2*Kpad] = [h | l], zero padded
 __global__ void split2_kernel(const float* __restrict__ src, long long node_stride, long long off, int rows, int K, int rows_pad, int Kpad,
                               __nv_bfloat16* __restrict__ out, int nb) {
@@ -645,6 +949,13 @@ struct FcState {
     unsigned long long* loss = nullptr;   // [P]
     float* s1 = nullptr; double* dj2 = nullptr; double* dot = nullptr;
     CUtensorMap tmX, tmW1, tmA2, tmW2, tmA3, tmW3, tmA4, tmW4;
+    // delta formulation (v3): node 0's pre-activations and activations, per-batch delta operands
+    __half *t1 = nullptr, *t2 = nullptr; float* t3 = nullptr;                  // [rows256, 512] / [rows256, 256] binary16, [rows256, 128] float32
+    __nv_bfloat16 *a2b = nullptr, *a3b = nullptr;                              // node 0's a^1, a^2, tile-major [h | l]
+    __nv_bfloat16 *dw1 = nullptr, *w2c = nullptr, *w3c = nullptr;              // [nb,512,832], [nb,256,1024], [nb,128,512]
+    float* dbias = nullptr;                                                    // [nb, 912]
+    __nv_bfloat16 *da1 = nullptr, *da2 = nullptr;                              // tile-major [nb][mb128][8][128][64], [nb][mb128][4][128][64]
+    CUtensorMap tmA2b, tmA3b, tmdW1, tmW2c, tmW3c, tmdA1, tmdA2;
     int version = 2;                   // 2: fc_gemm2_kernel ([h | l] operands, CTA pairs, persistent); 1: fc_gemm_kernel
 };
 
@@ -703,6 +1014,23 @@ static int launch_gemm2(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, 
     return PMP_OK;
 }
 
+template <int BN, int EPI, int NSTAGE>
+static int launch_gemm3(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& a0, const CUtensorMap& b, const Gemm3Args& g) {
+    constexpr size_t smem = (size_t)NSTAGE * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + (EPI == EPI3_L4_NLL ? (size_t)L4_NB * (H3 * 12 + H3 + NCLS_PAD) * sizeof(float) : 0);
+    static_assert(smem <= 227 * 1024 - 8 * 1024, "shared-memory plan of fc_gemm3_kernel");
+    if (EPI == EPI3_L4_NLL && g.nb > L4_NB) { set_error("FC delta sweep: at most %d nodes per batch (PMP_FC_BATCH)", L4_NB); return PMP_ERR_UNSUPPORTED; }
+    static bool attr = false;
+    if (!attr) { PMP_CUDA(cudaFuncSetAttribute(fc_gemm3_kernel<BN, EPI, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const long long tiles = (long long)((g.M + 2 * BM - 1) / (2 * BM)) * (g.n_total / BN) * g.nb;
+    long long pairs = c->sm_count / 2;
+    if (pairs > tiles) pairs = tiles;
+    if (pairs < 1) pairs = 1;
+    fc_gemm3_kernel<BN, EPI, NSTAGE><<<dim3((unsigned)(2 * pairs)), GEMM2_THREADS, smem, c->stream>>>(a, a0, b, g);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    return PMP_OK;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int n_total, int nb) {
     static bool attr = false;
@@ -715,7 +1043,8 @@ static int launch_gemm(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, c
 }
 
 static void free_state(FcState* s) {
-    void* ptrs[] = {s->xs, s->labels, s->w1, s->w2, s->w3, s->w4, s->bias, s->a2, s->a3, s->a4, s->loss, s->s1, s->dj2, s->dot};
+    void* ptrs[] = {s->xs, s->labels, s->w1, s->w2, s->w3, s->w4, s->bias, s->a2, s->a3, s->a4, s->loss, s->s1, s->dj2, s->dot,
+                    s->t1, s->t2, s->t3, s->a2b, s->a3b, s->dw1, s->w2c, s->w3c, s->dbias, s->da1, s->da2};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -828,6 +1157,34 @@ int pmp_set_data_fc(pmp_ctx* c, const float* X, const int64_t* labels, int64_t n
         if ((rc2 = make_map(&s->tmW2, s->w2, 2 * H1, H2, nb, 128))) return rc2;
         if ((rc2 = make_map_tiled(&s->tmA3, s->a3, 2 * H2 / 64, mb128, nb))) return rc2;
         if ((rc2 = make_map(&s->tmW3, s->w3, 2 * H2, H3, nb, 64))) return rc2;
+        // delta formulation: node 0's pre-activations / activations and the per-batch delta operands
+        const size_t rows256 = (size_t)((n_local + 255) / 256) * 256;
+        PMP_CUDA(cudaMalloc((void**)&s->t1, rows256 * H1 * sizeof(__half)));
+        PMP_CUDA(cudaMalloc((void**)&s->t2, rows256 * H2 * sizeof(__half)));
+        PMP_CUDA(cudaMalloc((void**)&s->t3, rows256 * H3 * sizeof(float)));
+        PMP_CUDA(cudaMalloc((void**)&s->a2b, (size_t)mb128 * 128 * 2 * H1 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->a3b, (size_t)mb128 * 128 * 2 * H2 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->dw1, (size_t)nb * H1 * D_IN_PAD * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->w2c, (size_t)nb * H2 * 2 * H1 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->w3c, (size_t)nb * H3 * 2 * H2 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->dbias, (size_t)nb * (H1 + H2 + H3 + NCLS_PAD) * sizeof(float)));
+        PMP_CUDA(cudaMalloc((void**)&s->da1, (size_t)nb * mb128 * 128 * H1 * 2));
+        PMP_CUDA(cudaMalloc((void**)&s->da2, (size_t)nb * mb128 * 128 * H2 * 2));
+        PMP_CUDA(cudaMemsetAsync(s->t1, 0, rows256 * H1 * sizeof(__half), c->stream));
+        PMP_CUDA(cudaMemsetAsync(s->t2, 0, rows256 * H2 * sizeof(__half), c->stream));
+        PMP_CUDA(cudaMemsetAsync(s->t3, 0, rows256 * H3 * sizeof(float), c->stream));
+        PMP_CUDA(cudaMemsetAsync(s->a2b, 0, (size_t)mb128 * 128 * 2 * H1 * 2, c->stream));
+        PMP_CUDA(cudaMemsetAsync(s->a3b, 0, (size_t)mb128 * 128 * 2 * H2 * 2, c->stream));
+        PMP_CUDA(cudaMemsetAsync(s->da1, 0, (size_t)nb * mb128 * 128 * H1 * 2, c->stream));
+        PMP_CUDA(cudaMemsetAsync(s->da2, 0, (size_t)nb * mb128 * 128 * H2 * 2, c->stream));
+        PMP_CUDA(cudaStreamSynchronize(c->stream));
+        if ((rc2 = make_map_tiled(&s->tmA2b, s->a2b, 2 * H1 / 64, mb128, 1))) return rc2;
+        if ((rc2 = make_map_tiled(&s->tmA3b, s->a3b, 2 * H2 / 64, mb128, 1))) return rc2;
+        if ((rc2 = make_map(&s->tmdW1, s->dw1, D_IN_PAD, H1, nb, 128))) return rc2;
+        if ((rc2 = make_map(&s->tmW2c, s->w2c, 2 * H1, H2, nb, 128))) return rc2;
+        if ((rc2 = make_map(&s->tmW3c, s->w3c, 2 * H2, H3, nb, 64))) return rc2;
+        if ((rc2 = make_map_tiled(&s->tmdA1, s->da1, H1 / 64, mb128, nb))) return rc2;
+        if ((rc2 = make_map_tiled(&s->tmdA2, s->da2, H2 / 64, mb128, nb))) return rc2;
         return PMP_OK;
     }
     PMP_CUDA(cudaMalloc((void**)&s->w1, (size_t)nb * H1 * 3 * D_IN_PAD * 2));
@@ -860,7 +1217,51 @@ int pmp_fc_loglik(pmp_ctx* c) {
     if (!s->loss) PMP_CUDA(cudaMalloc((void**)&s->loss, (size_t)MAX_NODES * sizeof(unsigned long long)));
     PMP_CUDA(cudaMemsetAsync(s->loss, 0, (size_t)P * sizeof(unsigned long long), c->stream));
     const int bias_stride = H1 + H2 + H3 + NCLS_PAD;
-    for (int p0 = 0; p0 < P; p0 += s->nb) {
+    // Contraction mode.  delta (v3, see fc_gemm3_kernel): needs proposals that are small increments about node 0 — generated by
+    // pmp_propose with alpha sqrt(depth) <= 1e-3 (the reference runs alpha = 1e-4, PMP_FC.py:15); anything else (caller-supplied nodes,
+    // large steps) takes the 3-product split (v2).  PMP_FC_MODE=x3 | delta overrides.
+    bool delta = s->version == 2 && s->nb <= L4_NB && !c->props_external && P > 1 &&
+                 (double)c->cfg.alpha * sqrt((double)(c->cfg.tree == PMP_TREE_FLAT ? 1 : c->cfg.depth)) <= 1e-3;
+    if (const char* m = getenv("PMP_FC_MODE")) { if (!strcmp(m, "x3")) delta = false; else if (!strcmp(m, "delta") && s->version == 2 && s->nb <= L4_NB) delta = true; }
+    if (delta) {
+        const float* th0 = c->d_props;                               // node 0 = the current state
+        const int mb128 = (M + 127) / 128;
+        long long t;
+        // ---- base pass: node 0 with the 3-product split; keeps t^1_0, t^2_0 (binary16), t^3_0 (float32), a^1_0, a^2_0 ([h | l]) ----
+        t = (long long)H1 * D_IN_PAD;   split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th0, THETA_DIM, OFF_W1, H1, D_IN, H1, D_IN_PAD, s->w1, 1);
+        t = (long long)H2 * H1;         split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th0, THETA_DIM, OFF_W2, H2, H1, H2, H1, s->w2, 1);
+        t = (long long)H3 * H2;         split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th0, THETA_DIM, OFF_W3, H3, H2, H3, H2, s->w3, 1);
+        gather_bias_kernel<<<(bias_stride + 255) / 256, 256, 0, c->stream>>>(th0, THETA_DIM, s->bias, 1);
+        c->launches += 4;
+        PMP_CUDA(cudaGetLastError());
+        Gemm2Args b1{}; b1.M = M; b1.Kpad = D_IN_PAD; b1.a_shared = 1; b1.n_total = H1; b1.nb = 1; b1.bias = s->bias; b1.bias_stride = bias_stride; b1.a_tiled = 0; b1.mb128 = mb128; b1.out = s->a2b; b1.t_out16 = s->t1;
+        if ((rc = launch_gemm2<256, EPI2_RELU_SPLIT, 3>(c, s->tmX, s->tmW1, b1))) return rc;
+        Gemm2Args b2{}; b2.M = M; b2.Kpad = H1; b2.n_total = H2; b2.nb = 1; b2.bias = s->bias + H1; b2.bias_stride = bias_stride; b2.a_tiled = 1; b2.mb128 = mb128; b2.out = s->a3b; b2.t_out16 = s->t2;
+        if ((rc = launch_gemm2<256, EPI2_RELU_SPLIT, 3>(c, s->tmA2b, s->tmW2, b2))) return rc;
+        Gemm2Args b3{}; b3.M = M; b3.Kpad = H2; b3.n_total = H3; b3.nb = 1; b3.bias = s->bias + H1 + H2; b3.bias_stride = bias_stride; b3.a_tiled = 1; b3.mb128 = mb128; b3.out = nullptr; b3.t_out32 = s->t3;
+        if ((rc = launch_gemm2<128, EPI2_RELU_SPLIT, 4>(c, s->tmA3b, s->tmW3, b3))) return rc;
+        // ---- every node (node 0 included: its increments are zero) through the one-product delta chain, nb nodes per launch ----
+        for (int p0 = 0; p0 < P; p0 += s->nb) {
+            const int nb = (P - p0) < s->nb ? (P - p0) : s->nb;
+            const float* th = c->d_props + (long long)p0 * THETA_DIM;
+            t = (long long)nb * H1 * D_IN_PAD;   delta_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, th0, THETA_DIM, OFF_W1, H1, D_IN, D_IN_PAD, 0, s->dw1, nb);
+            t = (long long)nb * H2 * H1;         delta_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, th0, THETA_DIM, OFF_W2, H2, H1, H1, 1, s->w2c, nb);
+            t = (long long)nb * H3 * H2;         delta_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, th0, THETA_DIM, OFF_W3, H3, H2, H2, 1, s->w3c, nb);
+            t = (long long)nb * bias_stride;     delta_bias_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, th0, THETA_DIM, s->dbias, nb);
+            c->launches += 4;
+            PMP_CUDA(cudaGetLastError());
+            Gemm3Args g1{}; g1.M = M; g1.nb = nb; g1.n_total = H1; g1.mb128 = mb128; g1.nk_a = D_IN_PAD / BK; g1.nk_total = D_IN_PAD / BK; g1.a_rowmajor = 1;
+            g1.dbias = s->dbias; g1.dbias_stride = bias_stride; g1.t0h = s->t1; g1.out = s->da1;
+            if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6>(c, s->tmX, s->tmX, s->tmdW1, g1))) return rc;
+            Gemm3Args g2{}; g2.M = M; g2.nb = nb; g2.n_total = H2; g2.mb128 = mb128; g2.nk_a = H1 / BK; g2.nk_total = 2 * H1 / BK; g2.a_rowmajor = 0;
+            g2.dbias = s->dbias + H1; g2.dbias_stride = bias_stride; g2.t0h = s->t2; g2.out = s->da2;
+            if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6>(c, s->tmdA1, s->tmA2b, s->tmW2c, g2))) return rc;
+            Gemm3Args g3{}; g3.M = M; g3.nb = nb; g3.n_total = H3; g3.mb128 = mb128; g3.nk_a = H2 / BK; g3.nk_total = 2 * H2 / BK; g3.a_rowmajor = 0;
+            g3.dbias = s->dbias + H1 + H2; g3.dbias_stride = bias_stride; g3.t0f = s->t3; g3.theta = th; g3.theta_stride = THETA_DIM; g3.labels = s->labels; g3.loss = s->loss + p0;
+            if ((rc = launch_gemm3<128, EPI3_L4_NLL, 6>(c, s->tmdA2, s->tmA3b, s->tmW3c, g3))) return rc;
+        }
+    }
+    for (int p0 = 0; p0 < P && !delta; p0 += s->nb) {
         const int nb = (P - p0) < s->nb ? (P - p0) : s->nb;
         const float* th = c->d_props + (long long)p0 * THETA_DIM;
         long long t;

@@ -93,8 +93,23 @@ static void drop_graph(pmp_ctx* c) {
 
 // ---- launches ------------------------------------------------------------------------------------------------
 static int launch_propose(pmp_ctx* c) {
+    c->props_external = false;
     ProposeArgs a{c->d_state, c->d_props, c->d_cnt, c->seed, c->P, c->cfg.dim, c->cfg.tree, c->cfg.b, c->cfg.depth, c->cfg.alpha, (c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0};
     long long total = (long long)c->P * c->cfg.dim;
+    if (c->cfg.tree != PMP_TREE_FLAT && total >= (1ll << 20) && c->cfg.dim >= 1024) {
+        // long parameter vectors on a tree: one launch per level, one quantile per element (propose_level_kernel)
+        const int b = c->cfg.tree == PMP_TREE_BINARY ? 2 : c->cfg.b;
+        unsigned gx = (unsigned)((c->cfg.dim + 1023) / 1024);
+        propose_level_kernel<<<dim3(gx, 1), 256, 0, c->stream>>>(a, 0);
+        c->launches++;
+        long long s = 1;
+        for (int l = 0; l < c->cfg.depth; ++l, s *= b) {
+            propose_level_kernel<<<dim3(gx, (unsigned)(s * (b - 1))), 256, 0, c->stream>>>(a, (int)s);
+            c->launches++;
+        }
+        PMP_CUDA(cudaGetLastError());
+        return PMP_OK;
+    }
     long long blocks = (total + 255) / 256;
     long long cap = (long long)c->sm_count * 8;
     if (blocks > cap) blocks = cap;
@@ -403,7 +418,7 @@ int pmp_destroy(pmp_ctx* c) {
     for (int r = 0; r < PEER_MAX_WORLD; ++r) if (c->peer_xchg[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_xchg[r]);
     if (c->d_xchg) cudaFree(c->d_xchg);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
-                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_bimg, c->d_kt_s1, c->d_kt_dj2, c->d_kt_dot};
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_hs, c->d_bimg, c->d_kt_s1, c->d_kt_dj2, c->d_kt_dot};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -577,6 +592,7 @@ int pmp_write_proposals(pmp_ctx* c, const float* in, int64_t count) {
     PMP_CUDA(cudaMemcpyAsync(c->d_props, in, count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     PMP_CUDA(cudaStreamSynchronize(c->stream));
     c->lt_valid = false;
+    c->props_external = true;
     return PMP_OK;
 }
 
@@ -716,6 +732,19 @@ int pmp_read_trace(pmp_ctx* c, int64_t max_iters, float* state, int32_t* next, i
     return PMP_OK;
 }
 
+// Hand-off buffers of the persistent kernels (zeroed once: tag 0 is never current).
+static int ensure_handoff(pmp_ctx* c, Handoff* out) {
+    const size_t nw = handoff_node_words(c->P), zw = handoff_z_words(c->P);
+    if (!c->d_hs || c->hs_P != c->P) {
+        if (c->d_hs) { PMP_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->d_hs); c->d_hs = nullptr; }
+        PMP_CUDA(cudaMalloc((void**)&c->d_hs, (nw + zw) * sizeof(unsigned long long)));
+        PMP_CUDA(cudaMemsetAsync(c->d_hs, 0, (nw + zw) * sizeof(unsigned long long), c->stream));
+        c->hs_words = nw + zw; c->hs_P = c->P;
+    }
+    out->nodes = c->d_hs; out->zt = c->d_hs + nw; out->epoch = c->hs_epoch;
+    return PMP_OK;
+}
+
 // Persistent cooperative chain loop (chain_persistent.cuh): single GPU, linear-Gaussian target, fast-acceptance rules, and a
 // data slice per CTA that fits shared memory.  Returns 1 when it ran, 0 when the stepwise path must be used, < 0 on error.
 static int try_run_persistent(pmp_ctx* c, int64_t iters) {
@@ -746,18 +775,23 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     pa.sync = reinterpret_cast<PersistSync*>(c->d_psync);
     pa.iters = (int)iters;
     pa.max_chunks = (int)max_chunks;
+    const bool hs = env_int("PMP_HANDOFF", 1) != 0;   // flag-in-data hand-offs (default) or release/acquire counters
+    if (hs && (rc = ensure_handoff(c, &pa.hs))) return rc;
     void* kargs[] = {&pa};
     const void* fn;
+#define PMP_SINGLE_FN(ALGO) (hs ? (const void*)chain_persistent_kernel<ALGO, true> : (const void*)chain_persistent_kernel<ALGO, false>)
     switch (c->cfg.algo) {
-        case PMP_ALGO_MP: fn = (const void*)chain_persistent_kernel<PMP_ALGO_MP>; break;
-        case PMP_ALGO_PSP: fn = (const void*)chain_persistent_kernel<PMP_ALGO_PSP>; break;
-        default: fn = (const void*)chain_persistent_kernel<PMP_ALGO_TABLE>; break;
+        case PMP_ALGO_MP: fn = PMP_SINGLE_FN(PMP_ALGO_MP); break;
+        case PMP_ALGO_PSP: fn = PMP_SINGLE_FN(PMP_ALGO_PSP); break;
+        default: fn = PMP_SINGLE_FN(PMP_ALGO_TABLE); break;
     }
+#undef PMP_SINGLE_FN
     PMP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, smem));
     if (per_sm < 1) return 0;
     PMP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PERSIST_THREADS), kargs, smem, c->stream));
+    if (hs) c->hs_epoch += (unsigned int)iters;
     c->launches++;
     c->host_iter += (unsigned long long)iters;
     c->z_valid_iter = -1;
@@ -986,6 +1020,7 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     const size_t accept_smem = lean_smem_bytes(c0->P, c0->cfg.algo);
     const size_t smem = sweep_smem > accept_smem ? sweep_smem : accept_smem;
     if (smem > 200 * 1024) { set_error("co-scheduled chains: a sweep CTA's data slice (%zu bytes) does not fit shared memory", smem); return PMP_ERR_UNSUPPORTED; }
+    const bool hs = env_int("PMP_HANDOFF", 1) != 0;
     std::unique_ptr<PersistMultiArgs> pa_owner(new PersistMultiArgs());      // per call: several host threads may drive different contexts (kernel parameters are copied at launch)
     PersistMultiArgs& pa = *pa_owner;
     int rc;
@@ -1002,20 +1037,24 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
         pa.ch[k].sync = reinterpret_cast<PersistSync*>(c->d_psync);
         pa.ch[k].xchg.world = c->world; pa.ch[k].xchg.me = c->rank; pa.ch[k].xchg.local = c->d_xchg; pa.ch[k].xchg.base = c->xchg_count;
         for (int r = 0; r < PEER_MAX_WORLD; ++r) pa.ch[k].xchg.peer[r] = c->peer_xchg[r];
+        if (hs && (rc = ensure_handoff(c, &pa.ch[k].hs))) return rc;
         PMP_CUDA(cudaStreamSynchronize(c->stream));                // everything queued on this chain's own stream is done before the joint launch
     }
     pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks; pa.n_accept = n_accept;
     void* kargs[] = {&pa};
     const void* fn;
-    int groups = env_int("PMP_MULTI_GROUPS", K >= 4 ? 4 : 2);                          // warp groups per sweep CTA
-    if (groups != 2 && groups != 4 && groups != 8) groups = K >= 4 ? 4 : 2;
-#define PMP_MULTI_FN(ALGO) (groups == 8 ? (const void*)chain_persistent_multi_kernel<ALGO, 8> : groups == 4 ? (const void*)chain_persistent_multi_kernel<ALGO, 4> : (const void*)chain_persistent_multi_kernel<ALGO, 2>)
+    const int groups_dflt = K >= 8 ? 8 : (K >= 4 ? 4 : 2);                             // warp groups per sweep CTA (measured, scripts/tune_multi.py)
+    int groups = env_int("PMP_MULTI_GROUPS", groups_dflt);
+    if (groups != 2 && groups != 4 && groups != 8) groups = groups_dflt;
+#define PMP_MULTI_FN2(ALGO, HSV) (groups == 8 ? (const void*)chain_persistent_multi_kernel<ALGO, 8, HSV> : groups == 4 ? (const void*)chain_persistent_multi_kernel<ALGO, 4, HSV> : (const void*)chain_persistent_multi_kernel<ALGO, 2, HSV>)
+#define PMP_MULTI_FN(ALGO) (hs ? PMP_MULTI_FN2(ALGO, true) : PMP_MULTI_FN2(ALGO, false))
     switch (c0->cfg.algo) {
         case PMP_ALGO_MP: fn = PMP_MULTI_FN(PMP_ALGO_MP); break;
         case PMP_ALGO_PSP: fn = PMP_MULTI_FN(PMP_ALGO_PSP); break;
         default: fn = PMP_MULTI_FN(PMP_ALGO_TABLE); break;
     }
 #undef PMP_MULTI_FN
+#undef PMP_MULTI_FN2
     PMP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, smem));
@@ -1029,6 +1068,7 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
         pmp_ctx* c = cs[k];
         if (k > 0) PMP_CUDA(cudaStreamWaitEvent(c->stream, c0->ev1, 0));   // later work on the chain's own stream is ordered after the joint kernel
         if (c->world > 1) c->xchg_count += (unsigned long long)iters;       // only once the launch is in the stream: a failed launch must not shift the tags
+        if (hs) c->hs_epoch += (unsigned int)iters;
         c->host_iter += (unsigned long long)iters;
         c->z_valid_iter = -1;
         c->lt_valid = false;

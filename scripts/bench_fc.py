@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import pmp_mcmc_b200 as pm
 from pmp_mcmc_b200 import _lib as L
-from oracle import oracle as o
+FC_DIM = 567434
 
 n = int(os.environ.get("N", 60000)); P = int(os.environ.get("P", 64)); reps = int(os.environ.get("REPS", 3))
 rng = np.random.default_rng(0)
@@ -21,9 +21,9 @@ if world > 1:                                     # torchrun: data rows sharded 
 else:
     c = pm.Context(0)
     lo, hi = 0, n
-c.configure(L.TREE_BINARY, depth=int(np.log2(P)), dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+c.configure(L.TREE_BINARY, depth=int(np.log2(P)), dim=FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
 c.set_data_fc(X[lo:hi], y[lo:hi], n_offset=lo, n_global=n)
-c.set_state(o.fc_init_theta(1)); c.seed(1, 0)
+c.set_state(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'fc_theta0.npy'))); c.seed(1, 0)
 import ctypes
 t0 = time.perf_counter(); c.propose(); c.sync(); t_prop = time.perf_counter() - t0
 c.loglik(read=False); c.sync()
@@ -44,7 +44,7 @@ if world > 1:
 if rank == 0:
   print(json.dumps({"n_gpus": world, "workload": "FC 784-512-256-128-10 log-target sweep, n=%d, P=%d (binary tree)" % (n, P), "seconds_per_sweep": dt, "proposal_evals_per_s": P / dt,
                   "propose_seconds": t_prop, "algorithmic_tflops": alg / dt / 1e12, "hardware_tflops_bf16x3": 3 * alg / dt / 1e12 * (2496 * 512 + 1536 * 256 + 768 * 128 + 384 * 16) / (3 * 566528.0),
-                  "roofline": {"bound": "tensor", "achieved": alg / dt / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": alg / dt / 1e12 / peak, "note": "algorithmic flops; the bf16x3 split executes ~3.1x as many"},
+                  "mode": os.environ.get("PMP_FC_MODE", "auto"), "roofline": {"bound": "tensor", "achieved": alg / dt / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": alg / dt / 1e12 / peak, "note": "algorithmic flops; the bf16x3 split executes ~3.1x as many"},
                   "lt_range": [float(lt.min()), float(lt.max())], "accepted": int(nxt)}))
 c.close()
 if world > 1:

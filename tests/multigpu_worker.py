@@ -118,7 +118,7 @@ def main():
     rng = np.random.default_rng(31)
     nf = 1500
     Xf = rng.standard_normal((nf, 784)).astype(np.float32); yf = rng.integers(0, 10, size=nf).astype(np.int64)
-    ctx.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-3, scale=10.0)
+    ctx.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
     lo, hi = pdist.shard_bounds(nf, world, rank, align=128)
     ctx.set_data_fc(Xf[lo:hi], yf[lo:hi], n_offset=lo, n_global=nf)
     ctx.set_state(o.fc_init_theta(2)); ctx.seed(21, 0); ctx.propose()

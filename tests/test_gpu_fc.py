@@ -13,10 +13,15 @@ def _data(n, seed=0):
     return X, y
 
 
+@pytest.mark.parametrize("mode", ["auto", "x3"])
 @pytest.mark.parametrize("n,P,alpha", [(300, 3, 1e-2), (2000, 5, 1e-4), (4133, 9, 1e-4)])
-def test_fc_logtarget_parity(ctx, n, P, alpha):
+def test_fc_logtarget_parity(ctx, n, P, alpha, mode, monkeypatch):
+    """mode auto: the one-product delta formulation (fc_gemm3_kernel) where the steps are small (alpha sqrt(depth) <= 1e-3), the 3-product
+    split otherwise; mode x3: the split everywhere.  Same bounds for both."""
     from oracle import oracle as o
     from pmp_mcmc_b200 import _lib as L
+    if mode != "auto":
+        monkeypatch.setenv("PMP_FC_MODE", mode)
     X, y = _data(n, seed=n)
     theta0 = o.fc_init_theta(1)
     ctx.configure(L.TREE_FLAT, b=P, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP if False else L.ALGO_TABLE, draw=L.DRAW_SINGLE,
@@ -126,9 +131,10 @@ def test_fc_device_resident_run_equals_stepwise(ctx):
     ctx.trace_config(0, 0)
 
 
+@pytest.mark.parametrize("mode", ["delta", "x3"])
 @pytest.mark.parametrize("tag", ["s", "full"])
 @pytest.mark.parametrize("kind", ["PMP", "MP"])
-def test_fc_trained_model_accepted_index_is_the_references(ctx, kind, tag):
+def test_fc_trained_model_accepted_index_is_the_references(ctx, kind, tag, mode, monkeypatch):
     """theta0 = the reference's FC_model.pkl, alpha = 1e-4 (PMP_FC.py:15,188-189), n = 384 and the BASELINE size n = 60 000: the device's
     losses against the reference's float32 loss(net), its standardised weights against the reference's B, and — for every injected uniform
     whose distance to a boundary of the reference's cdf exceeds the measured cdf discrepancy — the SAME accepted index as the reference's
@@ -137,6 +143,7 @@ def test_fc_trained_model_accepted_index_is_the_references(ctx, kind, tag):
     from conftest import ROOT
     from oracle import oracle as o
     from pmp_mcmc_b200 import _lib as L
+    monkeypatch.setenv("PMP_FC_MODE", mode)
     G = np.load(os.path.join(ROOT, "tests", "golden", "fc_step_trained.npz"))
     theta0 = np.load(os.path.join(ROOT, "tests", "golden", "fc_theta0.npy"))
     n = int(G[tag + "_n"])
@@ -173,3 +180,32 @@ def test_fc_trained_model_accepted_index_is_the_references(ctx, kind, tag):
             assert idx[0] == i_ref == nxt, (u, idx, i_ref)
             compared += 1
     assert compared >= 9, compared
+
+
+def test_fc_delta_and_split_contractions_agree_on_a_deep_tree(ctx, monkeypatch):
+    """P = 64 nodes of a depth-6 prefetch tree about the trained model: the one-product delta chain against the 3-product split and
+    against binary64 — log-targets, and the node differences that the acceptance is made of."""
+    import os
+    from conftest import ROOT
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    theta0 = np.load(os.path.join(ROOT, "tests", "golden", "fc_theta0.npy"))
+    n = 1000
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((n, 784)).astype(np.float32); y = rng.integers(0, 10, size=n).astype(np.int64)
+    out = {}
+    for mode in ("delta", "x3"):
+        monkeypatch.setenv("PMP_FC_MODE", mode)
+        ctx.configure(L.TREE_BINARY, depth=6, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+        ctx.set_data_fc(X, y); ctx.set_state(theta0); ctx.seed(9, 0); ctx.propose()
+        out[mode] = ctx.loglik()
+        assert np.array_equal(out[mode], ctx.loglik())            # integer loss sums: bitwise repeatable
+    props = ctx.read_proposals()
+    nodes = [0, 1, 2, 3, 17, 40, 63]
+    truth = np.array([-o.fc_mean_ce_f64(X, y, props[p]) / 10.0 for p in nodes])
+    for mode in ("delta", "x3"):
+        np.testing.assert_allclose(out[mode][nodes], truth, rtol=2e-5)
+        d_dev, d_true = out[mode][nodes][1:] - out[mode][0], truth[1:] - truth[0]
+        assert np.max(np.abs(d_dev - d_true)) <= 0.05 * np.max(np.abs(d_true)), (mode, d_dev, d_true)
+    dd, dx = out["delta"] - out["delta"][0], out["x3"] - out["x3"][0]
+    assert np.max(np.abs(dd - dx)) <= 0.05 * np.max(np.abs(dx))

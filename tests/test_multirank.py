@@ -90,7 +90,7 @@ def test_sharded_chain_equals_single_gpu_chain(tmp_path, world):
         rng = np.random.default_rng(31)
         nf = 1500
         Xf = rng.standard_normal((nf, 784)).astype(np.float32); yf = rng.integers(0, 10, size=nf).astype(np.int64)
-        c.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-3, scale=10.0)
+        c.configure(L.TREE_BINARY, depth=2, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
         c.set_data_fc(Xf, yf); c.set_state(o.fc_init_theta(2)); c.seed(21, 0); c.propose()
         assert np.array_equal(c.loglik(), g["fc_lt"])
         ng, dg = 5000, 20
