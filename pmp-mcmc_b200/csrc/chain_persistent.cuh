@@ -55,6 +55,49 @@ __device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target
     while ((int)(ld_acquire(p) - target) < 0) { if (++spins > 400000000u) __trap(); }
 }
 
+// Units of a sweep CTA.  With at least as many sweep CTAs as node tiles the CTAs are dealt to the tiles — tile t gets CTAs
+// [t * n_sweep / ntiles, (t + 1) * n_sweep / ntiles) — and split the tile's chunks evenly: ONE segment per CTA.  (Contiguous ranges of the
+// tile-major unit list made the 7 CTAs that straddle a tile boundary pay a second node fetch, a second flush and badly quantised chunk
+// rounds, and every iteration of the chain waited ~2 us for those stragglers; measured with PMP_DEBUG_STAMPS.)  The per-node sums are
+// integers, so the partition changes no bit.  Fewer CTAs than tiles: contiguous unit ranges, up to PERSIST_MAX_SEGS segments.
+struct SweepRange { int nseg; int tile[PERSIST_MAX_SEGS]; long long c0[PERSIST_MAX_SEGS], c1[PERSIST_MAX_SEGS]; };
+__host__ __device__ inline long long persist_max_chunks(int ntiles, long long nchunks, int n_sweep) {
+    if (n_sweep >= ntiles) { const int per_tile = n_sweep / ntiles; return (nchunks + per_tile - 1) / per_tile + 1; }
+    return ((long long)ntiles * nchunks + n_sweep - 1) / n_sweep + 1;
+}
+__device__ __forceinline__ void sweep_partition(int cta, int n_sweep, int ntiles, long long nchunks, SweepRange& r) {
+    r.nseg = 0;
+    if (nchunks == 0) return;
+    if (n_sweep >= ntiles) {
+        int t = (int)(((long long)cta * ntiles) / n_sweep);
+        while ((long long)(t + 1) * n_sweep / ntiles <= cta) ++t;       // tile whose CTA range [t n / T, (t+1) n / T) holds this CTA
+        while ((long long)t * n_sweep / ntiles > cta) --t;
+        const int first = (int)((long long)t * n_sweep / ntiles), cnt = (int)((long long)(t + 1) * n_sweep / ntiles) - first, k = cta - first;
+        const long long c0 = (long long)k * nchunks / cnt, c1 = (long long)(k + 1) * nchunks / cnt;
+        if (c1 > c0) { r.tile[0] = t; r.c0[0] = c0; r.c1[0] = c1; r.nseg = 1; }
+        return;
+    }
+    const long long units = (long long)ntiles * nchunks;
+    long long u = (long long)cta * units / n_sweep;
+    const long long u_end = (long long)(cta + 1) * units / n_sweep;
+    while (u < u_end && r.nseg < PERSIST_MAX_SEGS) {
+        const int ptile = (int)(u / nchunks);
+        const long long c0 = u - (long long)ptile * nchunks, c1 = min(nchunks, c0 + (u_end - u));
+        r.tile[r.nseg] = ptile; r.c0[r.nseg] = c0; r.c1[r.nseg] = c1;
+        u += c1 - c0; ++r.nseg;
+    }
+    if (u < u_end) __trap();               // units would be dropped silently: the host-side plan (persist_segments_fit) must have refused this shape
+}
+
+// One thread of a sweep CTA (or warp group) waits for the nodes of iteration `it` with a cheap hint — the tag of the last word the
+// acceptance CTA writes, polled with back-off — before the 128 fetch_node threads verify their own words: 128 threads per CTA polling
+// flat out (19 000 on the chip) took ~60 % of the L2 request rate and slowed the acceptance CTA's own loads and stores.
+__device__ __forceinline__ void wait_nodes_hint(const Handoff& hs, int P, unsigned long long tag) {
+    const unsigned long long* w = hs.nodes + 4ll * (P - 1) + 2;
+    SpinGuard sg;
+    while (!hs_tag_ok(ld_relaxed_gpu_u64(w), tag)) { __nanosleep(40); sg.tick(); }
+}
+
 template <int ALGO, bool HS>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(const __grid_constant__ PersistArgs pa) {
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -99,17 +142,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
 
     const int tp = tid & (TP - 1), td = tid / TP;
     const int ntiles = (a.P + PT - 1) / PT;
-    const long long units = (long long)ntiles * a.nchunks;
-    const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
 
-    // ---- stage this CTA's data slice once: segment s covers chunks [c_begin, c_end) of node tile ptile -----------------
-    int nseg = 0; int seg_tile[PERSIST_MAX_SEGS]; long long seg_c0[PERSIST_MAX_SEGS], seg_c1[PERSIST_MAX_SEGS]; int seg_slot[PERSIST_MAX_SEGS];
+    // ---- stage this CTA's data slice once: segment s covers chunks [c0, c1) of node tile ptile -----------------
+    SweepRange rg;
+    sweep_partition((int)blockIdx.x, n_sweep, ntiles, a.nchunks, rg);
+    const int nseg = rg.nseg;
+    int seg_tile[PERSIST_MAX_SEGS]; long long seg_c0[PERSIST_MAX_SEGS], seg_c1[PERSIST_MAX_SEGS]; int seg_slot[PERSIST_MAX_SEGS];
     {
-        long long u = u_begin; int slot = 0;
-        while (u < u_end && nseg < PERSIST_MAX_SEGS) {
-            int ptile = (int)(u / a.nchunks);
-            long long c0 = u - (long long)ptile * a.nchunks, c1 = min(a.nchunks, c0 + (u_end - u));
-            seg_tile[nseg] = ptile; seg_c0[nseg] = c0; seg_c1[nseg] = c1; seg_slot[nseg] = slot;
+        int slot = 0;
+        for (int sg = 0; sg < nseg; ++sg) {
+            const long long c0 = rg.c0[sg], c1 = rg.c1[sg];
+            seg_tile[sg] = rg.tile[sg]; seg_c0[sg] = c0; seg_c1[sg] = c1; seg_slot[sg] = slot;
             for (long long i = tid; i < (c1 - c0) * (CHUNK / 2); i += PERSIST_THREADS) {
                 int c = (int)(i / (CHUNK / 2)), k = (int)(i - (long long)c * (CHUNK / 2));
                 bool isy = k >= CHUNK / 4; int kk = isy ? k - CHUNK / 4 : k;
@@ -117,9 +160,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
                 const float* src = (isy ? a.y : a.x) + (g < a.n_local ? g : 0);
                 cp_async16(tile + (size_t)(slot + c) * CHUNK_STRIDE + (isy ? CHUNK : 0) + 4 * kk, src, g < a.n_local ? 16 : 0);
             }
-            slot += (int)(c1 - c0); u += c1 - c0; ++nseg;
+            slot += (int)(c1 - c0);
         }
-        if (u < u_end) __trap();               // units would be dropped silently: the host-side plan (persist_segments_fit) must have refused this shape
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
@@ -148,8 +190,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
                 }
             }
         }
-        if (HS && nseg == 0 && it > 0) {      // a CTA without units must not run ahead of the chain (its normals would overwrite a half still in use)
-            if (tid == 0) { float t0, t1, t2; fetch_node(pa.hs, a.theta, 0, a.P, false, tag, t0, t1, t2); }
+        if (HS && it > 0) {                   // (a CTA without units waits too: its normals of it + 2 would overwrite a half still in use)
+            if (tid == 0) wait_nodes_hint(pa.hs, a.P, tag);
             __syncthreads();
         }
         for (int s = 0; s < nseg; ++s) {

@@ -172,17 +172,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
     const int P = a0.P;
     const long long nchunks = a0.nchunks, n_local = a0.n_local;
     const int ntiles = (P + PT - 1) / PT;
-    const long long units = (long long)ntiles * nchunks;
-    const long long u_begin = (long long)blockIdx.x * units / n_sweep, u_end = (long long)(blockIdx.x + 1) * units / n_sweep;
 
-    // ---- stage this CTA's data slice once (all 1024 threads): segment s covers chunks [c_begin, c_end) of node tile ptile --
-    int nseg = 0; int seg_tile[PERSIST_MAX_SEGS]; long long seg_c0[PERSIST_MAX_SEGS], seg_c1[PERSIST_MAX_SEGS]; int seg_slot[PERSIST_MAX_SEGS];
+    // ---- stage this CTA's data slice once (all 1024 threads): segment s covers chunks [c0, c1) of node tile ptile (sweep_partition) --
+    SweepRange rg;
+    sweep_partition((int)blockIdx.x, n_sweep, ntiles, nchunks, rg);
+    const int nseg = rg.nseg;
+    int seg_tile[PERSIST_MAX_SEGS]; long long seg_c0[PERSIST_MAX_SEGS], seg_c1[PERSIST_MAX_SEGS]; int seg_slot[PERSIST_MAX_SEGS];
     {
-        long long u = u_begin; int slot = 0;
-        while (u < u_end && nseg < PERSIST_MAX_SEGS) {
-            int ptile = (int)(u / nchunks);
-            long long c0 = u - (long long)ptile * nchunks, c1 = min(nchunks, c0 + (u_end - u));
-            seg_tile[nseg] = ptile; seg_c0[nseg] = c0; seg_c1[nseg] = c1; seg_slot[nseg] = slot;
+        int slot = 0;
+        for (int sg = 0; sg < nseg; ++sg) {
+            const long long c0 = rg.c0[sg], c1 = rg.c1[sg];
+            seg_tile[sg] = rg.tile[sg]; seg_c0[sg] = c0; seg_c1[sg] = c1; seg_slot[sg] = slot;
             for (long long i = tid; i < (c1 - c0) * (CHUNK / 2); i += PERSIST_THREADS) {
                 int c = (int)(i / (CHUNK / 2)), k = (int)(i - (long long)c * (CHUNK / 2));
                 bool isy = k >= CHUNK / 4; int kk = isy ? k - CHUNK / 4 : k;
@@ -190,9 +190,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 const float* src = (isy ? a0.y : a0.x) + (g < n_local ? g : 0);
                 cp_async16(tile + (size_t)(slot + c) * CHUNK_STRIDE + (isy ? CHUNK : 0) + 4 * kk, src, g < n_local ? 16 : 0);
             }
-            slot += (int)(c1 - c0); u += c1 - c0; ++nseg;
+            slot += (int)(c1 - c0);
         }
-        if (u < u_end) __trap();               // see chain_persistent.cuh
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
@@ -222,8 +221,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                     }
                 }
             }
-            if (HS && nseg == 0 && it > 0) {      // a CTA without units must not run ahead of the chain
-                if (htid == 0) { float t0, t1, t2; fetch_node(hs, a.theta, 0, P, false, tag, t0, t1, t2); }
+            if (HS && it > 0) {                   // one thread per group waits for the chain's nodes (cheap hint, back-off); CTAs without units wait too
+                if (htid == 0) wait_nodes_hint(hs, P, tag);
                 group_sync<NG>(half);
             }
             bool sat = false;

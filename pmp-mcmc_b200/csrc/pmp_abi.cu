@@ -72,6 +72,7 @@ static int env_int(const char* name, int dflt) { const char* v = getenv(name); r
 // touches at most this many tiles.  The host refuses the persistent kernels when it could exceed the cap (the kernels trap if it ever does).
 static bool persist_segments_fit(long long units, int n_sweep, long long nchunks) {
     if (units == 0 || nchunks == 0) return true;
+    if ((long long)n_sweep * nchunks >= units) return true;      // at least as many sweep CTAs as node tiles: one segment per CTA (sweep_partition)
     const long long per_cta = (units + n_sweep - 1) / n_sweep;
     return (per_cta + nchunks - 2) / nchunks + 1 <= PERSIST_MAX_SEGS;
 }
@@ -756,7 +757,7 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     if (nchunks == 0 || n_sweep < 1) return 0;
     const int ntiles = (c->P + PERSIST_PT - 1) / PERSIST_PT;
     const long long units = (long long)ntiles * nchunks;
-    const long long max_chunks = (units + n_sweep - 1) / n_sweep + 1;
+    const long long max_chunks = persist_max_chunks(ntiles, nchunks, n_sweep);
     const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
     if (!lean_accept_ok(c) || !persist_segments_fit(units, n_sweep, nchunks)) return 0;
     const size_t accept_smem = lean_smem_bytes(c->P, c->cfg.algo);
@@ -966,7 +967,7 @@ static bool peer_fused_ok(pmp_ctx** cs, int K, int64_t iters) {
     const int n_sweep = c0->sm_count - (K < PERSIST_MAX_ACCEPT ? K : PERSIST_MAX_ACCEPT);
     if (nchunks == 0 || n_sweep < 1) return false;
     const long long units = (long long)((c0->P + PERSIST_PT - 1) / PERSIST_PT) * nchunks;
-    const size_t sweep_smem = (size_t)((units + n_sweep - 1) / n_sweep + 1) * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
+    const size_t sweep_smem = (size_t)persist_max_chunks((c0->P + PERSIST_PT - 1) / PERSIST_PT, nchunks, n_sweep) * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
     if (sweep_smem > 200 * 1024 || !persist_segments_fit(units, n_sweep, nchunks)) return false;
     for (int k = 0; k < K; ++k) {
         pmp_ctx* c = cs[k];
@@ -1014,7 +1015,7 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     PMP_REQUIRE(nchunks <= plan_chunks, "this rank's shard (%lld blocks of 64 points) exceeds the even split (%lld blocks): shard with dist.shard_bounds or set PMP_PEER_XCHG=0", nchunks, plan_chunks);
     PMP_REQUIRE(plan_chunks > 0 && n_sweep >= 1, "no data");
     const int ntiles = (c0->P + PERSIST_PT - 1) / PERSIST_PT;
-    const long long max_chunks = ((long long)ntiles * plan_chunks + n_sweep - 1) / n_sweep + 1;
+    const long long max_chunks = persist_max_chunks(ntiles, plan_chunks, n_sweep);
     PMP_REQUIRE(persist_segments_fit((long long)ntiles * plan_chunks, n_sweep, plan_chunks), "co-scheduled chains: a sweep CTA would span more than %d node tiles", PERSIST_MAX_SEGS);
     const size_t sweep_smem = (size_t)max_chunks * CHUNK_STRIDE * sizeof(float) + (size_t)PERSIST_TD * PERSIST_PT * sizeof(unsigned long long);
     const size_t accept_smem = lean_smem_bytes(c0->P, c0->cfg.algo);
