@@ -263,8 +263,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+// "This accumulator stage has been read": the TMEM loads are complete (tcgen05.wait::ld) before this instruction, and nothing else the
+// epilogue did has to be visible to the MMA thread — so the arrive is RELAXED.  (The default .release compiled to MEMBAR.ALL.GPU per warp
+// and tile: it made the hand-back of the accumulator wait for the epilogue's own global stores to reach HBM; ncu source page r2g.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1, EPI2_GLM = 2 };
@@ -713,9 +716,9 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const float* s_w4 = s_w4_all + batch * (H3 * 12);
             const float* s_b3 = s_b3_all + batch * H3;
             const float* s_b4 = s_b4_all + batch * NCLS_PAD;
-            mbar_wait(&tfull_bar[acc], use & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * CH);
+            // node 0's pre-activations do not depend on this tile's MMAs: the first chunk's loads are issued BEFORE the wait for the
+            // accumulator, the next chunk's before the current one is processed (the epilogue was bound by their L2 latency: ncu r2e)
             if (EPI == EPI3_DELTA_RELU) {
                 const int col0 = n_blk * BN + chalf * CH;
                 const float* db = g.dbias + (long long)batch * g.dbias_stride + col0;
@@ -723,13 +726,19 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const long long blk = (long long)batch * g.mb128 + (m_blk * 2 + (int)rank);
                 __nv_bfloat16* oblk = g.out + blk * (long long)kts * (128 * 64) + (long long)lrow * 64;
                 const __half* trow = g.t0h + (long long)(valid ? row : 0) * g.n_total + col0;
-#pragma unroll 1
+                uint4 tq[4], tn[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tq[q] = __ldg(reinterpret_cast<const uint4*>(trow) + q);
+                mbar_wait(&tfull_bar[acc], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
                 for (int cc = 0; cc < CH / 32; ++cc) {
+                    if (cc + 1 < CH / 32) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tn[q] = __ldg(reinterpret_cast<const uint4*>(trow + (cc + 1) * 32) + q);
+                    }
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
-                    uint4 tq[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tq[q] = __ldg(reinterpret_cast<const uint4*>(trow + cc * 32) + q);
                     const __half2* th2 = reinterpret_cast<const __half2*>(tq);
                     uint32_t dp[16];
 #pragma unroll
@@ -748,6 +757,8 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int q = 0; q < 4; ++q) d[q] = make_uint4(dp[4 * q], dp[4 * q + 1], dp[4 * q + 2], dp[4 * q + 3]);
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tq[q] = tn[q];
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -757,13 +768,19 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < NCLS / 2; ++c) z2[c] = chalf == 0 ? make_float2(s_b4[2 * c], s_b4[2 * c + 1]) : make_float2(0.f, 0.f);
                 const float* trow = g.t0f + (long long)(valid ? row : 0) * H3 + chalf * CH;
-#pragma unroll 1
+                float4 tq[8], tn[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tq[q] = __ldg(reinterpret_cast<const float4*>(trow) + q);
+                mbar_wait(&tfull_bar[acc], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
                 for (int cc = 0; cc < CH / 32; ++cc) {
+                    if (cc + 1 < CH / 32) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) tn[q] = __ldg(reinterpret_cast<const float4*>(trow + (cc + 1) * 32) + q);
+                    }
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
-                    float4 tq[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) tq[q] = __ldg(reinterpret_cast<const float4*>(trow + cc * 32) + q);
                     const float* t0 = reinterpret_cast<const float*>(tq);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -777,6 +794,8 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         z2[2] = ffma2f(aa, make_float2(w1.x, w1.y), z2[2]); z2[3] = ffma2f(aa, make_float2(w1.z, w1.w), z2[3]);
                         z2[4] = ffma2f(aa, w2, z2[4]);
                     }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tq[q] = tn[q];
                 }
                 float z[NCLS];
 #pragma unroll
