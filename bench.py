@@ -40,7 +40,7 @@ sys.path.insert(0, ROOT)
 P_NODES = 1024
 N_DATA = 100000
 ITERS_PER_STEP = 1000
-CHAINS = 16
+CHAINS = 0           # co_scheduled block: 0 = 16 chains per GPU at --gpus 1 and 2, 24 at 4 and 8 (measured, scripts/tune_multi.py)
 SCALE = 1000.0
 ALPHA = 0.01
 METRIC = "proposal-evals/sec"
@@ -454,7 +454,7 @@ def main():
 
     # ---- K independent chains co-scheduled in one cooperative kernel (per GPU; sharded like the single chain when N > 1) --------
     co = None
-    chains = max(2, min(32, args.chains))
+    chains = max(2, min(32, args.chains)) if args.chains > 0 else (16 if world <= 2 else 24)
     if "co" not in skip:
         ctxs = [ctx]
         for k in range(1, chains):

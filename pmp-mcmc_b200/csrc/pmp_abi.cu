@@ -1005,7 +1005,9 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
     // the acceptances — not the sweeps — bound the throughput as soon as a sweep is short (measured, n = 12 500, K = 8: 6.2 us per chain
     // iteration with 2 acceptance CTAs, 2.8 us with 8).  PMP_MULTI_ACCEPT overrides (1..min(K, PERSIST_MAX_ACCEPT)).
     const int acc_cap = K < PERSIST_MAX_ACCEPT ? K : PERSIST_MAX_ACCEPT;
-    int n_accept = c0->world > 1 ? acc_cap : (K < 4 ? K : (K <= 8 ? 4 : acc_cap / 2));        // one GPU, full dataset: one per two chains suffices (10.4 vs 11.0 us per chain iteration at K = 8)
+    // measured (scripts/tune_multi.py, K x acceptance CTAs x groups at n = 100 000 / N): one GPU with the full dataset: K / 4 (K = 16: 10.2 us per
+    // chain iteration with 4, 10.8 with 8); a shard: K / 2 (n = 12 500, K = 24: 1.73 us with 12, 1.97 with 24, 2.08 with 6)
+    int n_accept = c0->world > 1 ? (K <= 2 ? K : (K / 2 < acc_cap ? K / 2 : acc_cap)) : (K < 4 ? K : (K / 4 < acc_cap ? K / 4 : acc_cap));
     { const int ov = env_int("PMP_MULTI_ACCEPT", 0); if (ov >= 1 && ov <= acc_cap) n_accept = ov; }
     const int G = c0->sm_count, n_sweep = G - n_accept;
     // world > 1: the kernel's shared-memory plan follows the LARGEST shard of any rank (rank-independent, see peer_fused_ok); this rank's own
