@@ -28,6 +28,11 @@ struct ChainArgs {
     int iters;
 };
 
+// Scratch of a chain (tree nodes, log-targets, weights / cdf, level scratch, draws): P * (4 dim + 28) bytes.  SM = true keeps it in SHARED
+// memory ([slot][thread]: conflict-free) — round 1 kept it in global memory, and with 2^20 chains it spilled out of L2: 11.8 GB of DRAM
+// writes per launch against 3.2 GB of recorded samples (ncu r1c).  SM = false is the fallback for trees too large for shared memory.
+__host__ __device__ inline size_t chain_scratch_bytes(int P, int dim) { return (size_t)P * (4 * (size_t)dim + 28); }
+
 __device__ __forceinline__ double chain_log_kernel(const float* nodes, long long nc, int dim, int a, int b, long long c, double ks, double lnk) {
     double s = 0.0;
     for (int j = 0; j < dim; ++j) {
@@ -37,12 +42,19 @@ __device__ __forceinline__ double chain_log_kernel(const float* nodes, long long
     return dim * lnk - 0.5 * s / (ks * ks);
 }
 
+template <bool SM>
 __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
+    extern __shared__ __align__(16) unsigned char chain_sm[];
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_chains) return;
     const pmp_config& cfg = a.cfg;
     const int P = a.P, dim = cfg.dim;
     const long long nc = a.n_chains;
+    // scratch addressing: element e of an array lives at [e * sn + so]
+    const long long sn = SM ? (long long)blockDim.x : nc, so = SM ? (long long)threadIdx.x : c;
+    double* const work = SM ? reinterpret_cast<double*>(chain_sm) : a.work;
+    float* const nodes = SM ? reinterpret_cast<float*>(chain_sm + (size_t)3 * P * blockDim.x * sizeof(double)) : a.nodes;
+    int* const draws = SM ? reinterpret_cast<int*>(chain_sm + (size_t)3 * P * blockDim.x * sizeof(double) + (size_t)P * dim * blockDim.x * sizeof(float)) : a.draws;
     const int b = (cfg.tree == PMP_TREE_BINARY) ? 2 : cfg.b;
     const int D = (cfg.tree == PMP_TREE_FLAT) ? 1 : cfg.depth;
     const double ks = (double)cfg.kernel_sigma;
@@ -50,11 +62,11 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
     const bool use_kernel = !(cfg.flags & PMP_FLAG_NO_KERNEL_TERM);
     const int uniform = (cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0;
     const unsigned long long cbase = (unsigned long long)c << 32;
-    double* lt = a.work;
-    double* A = a.work + (long long)P * nc;
-    double* tmp = a.work + 2ll * P * nc;
-#define NODE(p, j) a.nodes[((long long)(p) * dim + (j)) * nc + c]
-#define W(arr, p) arr[(long long)(p) * nc + c]
+    double* lt = work;
+    double* A = work + (long long)P * sn;
+    double* tmp = work + 2ll * P * sn;
+#define NODE(p, j) nodes[((long long)(p) * dim + (j)) * sn + so]
+#define W(arr, p) arr[(long long)(p) * sn + so]
 
     for (int it = 0; it < a.iters; ++it) {
         const unsigned long long iter = a.iter0 + (unsigned long long)it;
@@ -69,7 +81,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             }
         }
         // ---- log-targets
-        for (int p = 0; p < P; ++p) W(lt, p) = analytic_logtarget(cfg.target, &NODE(p, 0), (int)nc, dim, cfg.target_p0, cfg.target_p1) / (double)cfg.scale;
+        for (int p = 0; p < P; ++p) W(lt, p) = analytic_logtarget(cfg.target, &NODE(p, 0), (int)sn, dim, cfg.target_p0, cfg.target_p1) / (double)cfg.scale;
         // ---- log-weights
         int next;
         int n_draws = (cfg.draw == PMP_DRAW_SINGLE) ? 1 : P;
@@ -78,13 +90,13 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             double l0 = W(lt, 0), l1 = W(lt, 1);
             if (cfg.algo == PMP_ALGO_MH) next = u < exp((double)cfg.mh_temperature * (l1 - l0));
             else { double m = fmax(l0, l1); double w0 = exp(l0 - m), w1 = exp(l1 - m); next = (w1 / (w0 + w1)) > u; }
-            W(a.draws, 0) = next; n_draws = 1;
+            W(draws, 0) = next; n_draws = 1;
             W(A, 0) = l0; W(A, 1) = l1;
         } else {
             if (cfg.algo == PMP_ALGO_MP) {
                 for (int j = 0; j < P; ++j) {
                     double v = W(lt, j);
-                    if (use_kernel) for (int k = 0; k < P; ++k) if (k != j) v += chain_log_kernel(a.nodes, nc, dim, j, k, c, ks, lnk);
+                    if (use_kernel) for (int k = 0; k < P; ++k) if (k != j) v += chain_log_kernel(nodes, sn, dim, j, k, so, ks, lnk);
                     W(A, j) = v;
                 }
             } else if (cfg.algo == PMP_ALGO_PSP) {
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                         for (int j = 0; j < b; ++j) {
                             int nj = (int)(h + j * s);
                             double v = W(lt, nj);
-                            if (use_kernel) for (int k = 0; k < b; ++k) if (k != j) v += chain_log_kernel(a.nodes, nc, dim, nj, (int)(h + k * s), c, ks, lnk);
+                            if (use_kernel) for (int k = 0; k < b; ++k) if (k != j) v += chain_log_kernel(nodes, sn, dim, nj, (int)(h + k * s), so, ks, lnk);
                             W(tmp, nj) = v; mx = fmax(mx, v);
                         }
                         double se = 0.0;
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                         long long s = 1;
                         for (int d = 0; d < D; ++d) {
                             long long m = p % (s * b), h = m % s;
-                            for (int k = 0; k < b; ++k) { long long o = h + k * s; if (o != m) v += chain_log_kernel(a.nodes, nc, dim, (int)m, (int)o, c, ks, lnk); }
+                            for (int k = 0; k < b; ++k) { long long o = h + k * s; if (o != m) v += chain_log_kernel(nodes, sn, dim, (int)m, (int)o, so, ks, lnk); }
                             s *= b;
                         }
                     }
@@ -149,18 +161,18 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                 double thr = u64_to_unit(stream_u64(a.seed, iter, STREAM_DRAW, cbase | (unsigned long long)t)) * total;
                 int lo = 0, hi = P;
                 while (lo < hi) { int mid = (lo + hi) >> 1; double v = W(A, mid); bool go = right ? (v <= thr) : (v < thr); if (go) lo = mid + 1; else hi = mid; }
-                W(a.draws, t) = min(lo, P - 1);
+                W(draws, t) = min(lo, P - 1);
             }
             if (cfg.draw == PMP_DRAW_PYTHON) {
                 double up = u64_to_unit(stream_u64(a.seed, iter, STREAM_PICK, cbase));
-                next = W(a.draws, min(P - 1, (int)(up * (double)P)));
-            } else next = W(a.draws, 0);
+                next = W(draws, min(P - 1, (int)(up * (double)P)));
+            } else next = W(draws, 0);
         }
         // ---- record the resampled points (chain-fastest: coalesced 4-byte stores across the warp), new state
         if (a.samples) {
             float* out = a.samples + (long long)it * P * dim * nc;
             for (int t = 0; t < P; ++t) {
-                int src = t < n_draws ? W(a.draws, t) : next;
+                int src = t < n_draws ? W(draws, t) : next;
                 for (int j = 0; j < dim; ++j) out[((long long)t * dim + j) * nc + c] = NODE(src, j);
             }
         }
@@ -246,7 +258,17 @@ static int chains_launch(pmp_ctx* c, int64_t iters, int record) {
     }
     ChainArgs a{c->cfg, c->P, c->n_chains, c->d_chain_states, s->nodes, s->work, s->draws, record ? c->d_chain_samples : nullptr,
                 c->seed, c->chain_iteration, (int)iters};
-    chains_kernel<<<(unsigned)((c->n_chains + 127) / 128), 128, 0, c->stream>>>(a);
+    // scratch in shared memory when a block of >= 32 chains fits ~96 KB (two blocks per SM), else in global memory
+    const size_t per_chain = chain_scratch_bytes(c->P, c->cfg.dim);
+    int threads = 128;
+    while (threads > 32 && per_chain * threads > 96 * 1024) threads >>= 1;
+    const bool in_smem = per_chain * threads <= 96 * 1024 && !getenv("PMP_CHAINS_GLOBAL_SCRATCH");
+    if (in_smem) {
+        const size_t smem = per_chain * threads;
+        static size_t attr_set = 0;
+        if (smem > attr_set) { PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = 100 * 1024; }
+        chains_kernel<true><<<(unsigned)((c->n_chains + threads - 1) / threads), threads, smem, c->stream>>>(a);
+    } else chains_kernel<false><<<(unsigned)((c->n_chains + 127) / 128), 128, 0, c->stream>>>(a);
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     c->chain_iteration += (unsigned long long)iters;
