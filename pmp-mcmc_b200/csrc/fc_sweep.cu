@@ -117,7 +117,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) fc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; pointer arithmetic on the shared array keeps the shared address space (an integer round trip made every later load a generic LD.E)
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
@@ -311,7 +311,7 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;       // Ah, Al, Bh, Bl
     constexpr int TMEM_COLS = 2 * BN;                            // two accumulator stages
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; pointer arithmetic on the shared array keeps the shared address space (an integer round trip made every later load a generic LD.E)
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_w4[EPI == EPI2_L4_NLL ? H3 * 12 : 4];
@@ -621,7 +621,7 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 2 * BN;
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; pointer arithmetic on the shared array keeps the shared address space (an integer round trip made every later load a generic LD.E)
     __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
     // L4_NLL: the last layer (transposed, 12-float rows), the layer-3 bias increments and the last bias of ALL nodes of the batch, loaded once
