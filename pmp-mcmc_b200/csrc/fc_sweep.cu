@@ -612,8 +612,39 @@ struct Gemm3Args {
     unsigned long long* loss; // [nb] fixed-point sums
 };
 
-template <int BN, int EPI, int NSTAGE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
+// MC (operand multicast over a cluster of TWO CTA pairs; cluster dims are set at launch; OPT-IN, measured slower — see pmp_fc_loglik): the delta
+// kernels are bound by L2 -> SM delivery (one product per stage: 64 B/clk/SM wanted at full tensor rate against ~35-43 delivered, ncu r2c/r2g);
+// the idea was to cut the bytes per flop:
+//   MC = 1  the two pairs of a cluster take the two 256-column halves of the same (row block, node): the A tile (data rows) is the same, each
+//           CTA loads HALF of it (64 rows) and TMA-multicasts it to its counterpart in the other pair         (layer 1: 24 KB per stage, not 32)
+//   MC = 2  the two pairs take two consecutive row blocks of the same node: the B tile (weights) is the same, each CTA loads half of its
+//           half and multicasts it                                                                             (layer 2: 24 KB, not 32)
+// With multicast every CTA tracks the bytes landing in ITS OWN shared memory on its own full barrier (plain TMA, no cta_group); the
+// non-leader CTA of a pair relays "my operands are in" to the leader (one remote arrive per stage), and a stage is free again when BOTH
+// pairs' MMAs have consumed it (each leader's commit arrives on the empty barrier of all four CTAs).
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_plain(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// the same destination offset and the same mbarrier offset in every CTA of `mask`
+__device__ __forceinline__ void tma_load_3d_mcast(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BN, int EPI, int NSTAGE, int MC>
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
 fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB, const Gemm3Args g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int BH = BN / 2;
@@ -621,8 +652,8 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 2 * BN;
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; pointer arithmetic on the shared array keeps the shared address space (an integer round trip made every later load a generic LD.E)
-    __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; pointer arithmetic on the shared array keeps the shared address space
+    __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], ready_bar[NSTAGE], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
     // L4_NLL: the last layer (transposed, 12-float rows), the layer-3 bias increments and the last bias of ALL nodes of the batch, loaded once
     float* s_w4_all = reinterpret_cast<float*>(smem + (size_t)NSTAGE * STAGE_BYTES);           // [L4_NB][H3 * 12]
@@ -631,15 +662,24 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ float s_z[EPI == EPI3_L4_NLL ? BM * (NCLS + 1) : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();                    // 0..1, or 0..3 with multicast
+    const uint32_t rank = crank & 1u;                            // within the CTA pair
+    const uint32_t q = MC ? (crank >> 1) : 0u;                   // pair within the cluster
+    const uint32_t lead = crank & ~1u;                           // cluster rank of my pair's leader
     const int nblk_n = g.n_total / BN;
-    const int inner = nblk_n * g.nb;
-    const int total = ((g.M + 2 * BM - 1) / (2 * BM)) * inner;
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int mblks = (g.M + 2 * BM - 1) / (2 * BM);
+    // work items: MC = 0: one (row block, column block, node) tile per pair, node fastest; MC > 0: one super-tile per cluster, split over its pairs
+    const int total = MC == 0 ? mblks * nblk_n * g.nb : (MC == 1 ? mblks * g.nb : ((mblks + 1) / 2) * g.nb);
+    const int unit = MC ? (int)(blockIdx.x >> 2) : (int)(blockIdx.x >> 1), nunits = MC ? (int)(gridDim.x >> 2) : (int)(gridDim.x >> 1);
     const int num_k = g.nk_total;
+    auto decode = [&](int t, int& m_blk, int& n_blk, int& batch) {
+        if (MC == 0) { const int inner = nblk_n * g.nb; m_blk = t / inner; const int r = t - m_blk * inner; n_blk = r % nblk_n; batch = r / nblk_n; }
+        else if (MC == 1) { m_blk = t / g.nb; batch = t - m_blk * g.nb; n_blk = (int)q; }
+        else { const int mb2 = t / g.nb; batch = t - mb2 * g.nb; m_blk = 2 * mb2 + (int)q; n_blk = 0; }
+    };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); mbar_init(&ready_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * GEMM2_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -654,51 +694,76 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        if (lane == 0) {                                         // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {                                         // ===== TMA producer (every CTA) =====
             uint32_t it = 0;
-            for (int t = pair; t < total; t += npairs) {
-                const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
+            for (int t = unit; t < total; t += nunits) {
+                int m_blk, n_blk, batch; decode(t, m_blk, n_blk, batch);
                 const int row0 = m_blk * 2 * BM + (int)rank * BM, col0 = n_blk * BN + (int)rank * BH;
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const uint32_t s = it % NSTAGE, round = it / NSTAGE;
                     if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
-                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                    if (g.a_rowmajor) tma_load_3d_2sm(st, &tmA, lbar, kb * BK, row0, 0);
-                    else if (kb < g.nk_a) tma_load_5d_2sm(st, &tmA, lbar, 0, 0, kb, m_blk * 2 + (int)rank, batch);
-                    else tma_load_5d_2sm(st, &tmA0, lbar, 0, 0, kb - g.nk_a, m_blk * 2 + (int)rank, 0);
-                    tma_load_3d_2sm(st + A_BYTES, &tmB, lbar, kb * BK, col0, batch);
+                    if (MC == 0) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                        const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                        if (g.a_rowmajor) tma_load_3d_2sm(st, &tmA, lbar, kb * BK, row0, 0);
+                        else if (kb < g.nk_a) tma_load_5d_2sm(st, &tmA, lbar, 0, 0, kb, m_blk * 2 + (int)rank, batch);
+                        else tma_load_5d_2sm(st, &tmA0, lbar, 0, 0, kb - g.nk_a, m_blk * 2 + (int)rank, 0);
+                        tma_load_3d_2sm(st + A_BYTES, &tmB, lbar, kb * BK, col0, batch);
+                    } else {
+                        const uint32_t bar = smem_u32(&full_bar[s]);
+                        const uint16_t both = (uint16_t)((1u << rank) | (1u << (2u + rank)));       // me and my counterpart in the other pair
+                        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);                          // the bytes landing in MY shared memory
+                        if (MC == 1) {        // A shared: my half (64 rows) of the 128-row tile to both; B: my own half-tile (tmA0 = the data map with 64-row boxes)
+                            tma_load_3d_mcast(st + q * (A_BYTES / 2), &tmA0, bar, kb * BK, row0 + (int)q * (BM / 2), 0, both);
+                            tma_load_3d_plain(st + A_BYTES, &tmB, bar, kb * BK, col0, batch);
+                        } else {              // B shared: my half of my half-tile to both (tmB has BH/2-row boxes); A: my own tile
+                            if (kb < g.nk_a) tma_load_5d(st, &tmA, bar, 0, 0, kb, m_blk * 2 + (int)rank, batch);
+                            else tma_load_5d(st, &tmA0, bar, 0, 0, kb - g.nk_a, m_blk * 2 + (int)rank, 0);
+                            tma_load_3d_mcast(st + A_BYTES + q * (B_BYTES / 2), &tmB, bar, kb * BK, col0 + (int)q * (BH / 2), batch, both);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {                            // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {                            // ===== MMA issuer (leader CTA of every pair) =====
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            const uint16_t pair_mask = (uint16_t)(3u << lead), stage_mask = MC ? (uint16_t)0xF : (uint16_t)3;
             uint32_t it = 0; int j = 0;
-            for (int t = pair; t < total; t += npairs, ++j) {
+            for (int t = unit; t < total; t += nunits, ++j) {
                 const int acc = j & 1, use = j >> 1;
                 if (use > 0) { mbar_wait(&tempty_bar[acc], (use - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const uint32_t s = it % NSTAGE, round = it / NSTAGE;
                     mbar_wait(&full_bar[s], round & 1);
+                    if (MC) mbar_wait(&ready_bar[s], round & 1);            // the peer CTA's operands are in too
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint8_t* st = smem + s * STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(st), db = umma_desc_sw128(st + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2sm(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kb | k) != 0);
-                    umma_commit_2sm(&empty_bar[s]);
+                    umma_commit_mask(&empty_bar[s], stage_mask);
                 }
-                umma_commit_2sm(&tfull_bar[acc]);
+                umma_commit_mask(&tfull_bar[acc], pair_mask);
+            }
+        } else if (MC && lane == 0 && rank == 1) {               // ===== relay (non-leader CTA): "my operands are in" -> the leader's ready barrier
+            uint32_t it = 0;
+            for (int t = unit; t < total; t += nunits) {
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const uint32_t s = it % NSTAGE, round = it / NSTAGE;
+                    mbar_wait(&full_bar[s], round & 1);
+                    mbar_arrive_remote_release(mapa_u32(smem_u32(&ready_bar[s]), lead));
+                }
             }
         }
-    } else {                                                     // ===== epilogue warps 2..9 (both CTAs) =====
+    } else {                                                     // ===== epilogue warps 2..9 (every CTA) =====
         const int quarter = warp & 3;
         const int chalf = (warp - 2) >> 2;
         const int et = (warp - 2) * 32 + lane;
         constexpr int CH = BN / 2;
-        const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+        const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), lead), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), lead);
         if (EPI == EPI3_L4_NLL) {                                // once per launch: every node's 128 -> 10 layer into shared memory
             for (int b = 0; b < g.nb; ++b) {
                 const float* th = g.theta + (long long)b * g.theta_stride;
@@ -709,8 +774,8 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         int j = 0;
-        for (int t = pair; t < total; t += npairs, ++j) {
-            const int m_blk = t / inner, r = t - m_blk * inner, n_blk = r % nblk_n, batch = r / nblk_n;
+        for (int t = unit; t < total; t += nunits, ++j) {
+            int m_blk, n_blk, batch; decode(t, m_blk, n_blk, batch);
             const int acc = j & 1, use = j >> 1;
             const int lrow = quarter * 32 + lane;
             const int row = m_blk * 2 * BM + (int)rank * BM + lrow;
@@ -977,6 +1042,7 @@ struct FcState {
     float* dbias = nullptr;                                                    // [nb, 912]
     __nv_bfloat16 *da1 = nullptr, *da2 = nullptr;                              // tile-major [nb][mb128][8][128][64], [nb][mb128][4][128][64]
     CUtensorMap tmA2b, tmA3b, tmdW1, tmW2c, tmW3c, tmdA1, tmdA2;
+    CUtensorMap tmX64, tmW2c64;                                                // 64-row boxes: the halves that the multicast kernels load
     int version = 2;                   // 2: fc_gemm2_kernel ([h | l] operands, CTA pairs, persistent); 1: fc_gemm_kernel
 };
 
@@ -1035,20 +1101,40 @@ static int launch_gemm2(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& b, 
     return PMP_OK;
 }
 
-template <int BN, int EPI, int NSTAGE>
+template <int BN, int EPI, int NSTAGE, int MC>
 static int launch_gemm3(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& a0, const CUtensorMap& b, const Gemm3Args& g) {
     constexpr size_t smem = (size_t)NSTAGE * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + (EPI == EPI3_L4_NLL ? (size_t)L4_NB * (H3 * 12 + H3 + NCLS_PAD) * sizeof(float) : 0);
     static_assert(smem <= 227 * 1024 - 8 * 1024, "shared-memory plan of fc_gemm3_kernel");
     if (EPI == EPI3_L4_NLL && g.nb > L4_NB) { set_error("FC delta sweep: at most %d nodes per batch (PMP_FC_BATCH)", L4_NB); return PMP_ERR_UNSUPPORTED; }
     static bool attr = false;
-    if (!attr) { PMP_CUDA(cudaFuncSetAttribute(fc_gemm3_kernel<BN, EPI, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    const long long tiles = (long long)((g.M + 2 * BM - 1) / (2 * BM)) * (g.n_total / BN) * g.nb;
-    long long pairs = c->sm_count / 2;
-    if (pairs > tiles) pairs = tiles;
-    if (pairs < 1) pairs = 1;
-    fc_gemm3_kernel<BN, EPI, NSTAGE><<<dim3((unsigned)(2 * pairs)), GEMM2_THREADS, smem, c->stream>>>(a, a0, b, g);
+    if (!attr) {
+        PMP_CUDA(cudaFuncSetAttribute(fc_gemm3_kernel<BN, EPI, NSTAGE, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    constexpr int CL = MC ? 4 : 2;                                // CTAs per cluster: one pair, or two pairs sharing an operand by TMA multicast
+    const int mblks = (g.M + 2 * BM - 1) / (2 * BM), nblk_n = g.n_total / BN;
+    const long long units = MC == 0 ? (long long)mblks * nblk_n * g.nb : (MC == 1 ? (long long)mblks * g.nb : (long long)((mblks + 1) / 2) * g.nb);
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(GEMM2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // persistent kernel with a static schedule: every cluster must be resident at once.  Clusters of 4 do not tile every GPC (SM counts per
+    // GPC are not multiples of 4), so ask the driver how many fit instead of assuming sm_count / 4
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        cfg.gridDim = dim3((unsigned)(CL * (c->sm_count / CL)));
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fc_gemm3_kernel<BN, EPI, NSTAGE, MC>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = c->sm_count / CL / 2; }
+        max_clusters = n < c->sm_count / CL ? n : c->sm_count / CL;
+    }
+    if (getenv("PMP_FC_VERBOSE")) fprintf(stderr, "fc_gemm3<%d,%d,%d,MC=%d>: %d resident clusters of %d CTAs\n", BN, EPI, NSTAGE, MC, max_clusters, CL);
+    long long clusters = max_clusters;
+    if (clusters > units) clusters = units;
+    if (clusters < 1) clusters = 1;
+    cfg.gridDim = dim3((unsigned)(CL * clusters));
+    PMP_CUDA(cudaLaunchKernelEx(&cfg, fc_gemm3_kernel<BN, EPI, NSTAGE, MC>, a, a0, b, g));
     c->launches++;
-    PMP_CUDA(cudaGetLastError());
     return PMP_OK;
 }
 
@@ -1206,6 +1292,8 @@ int pmp_set_data_fc(pmp_ctx* c, const float* X, const int64_t* labels, int64_t n
         if ((rc2 = make_map(&s->tmW3c, s->w3c, 2 * H2, H3, nb, 64))) return rc2;
         if ((rc2 = make_map_tiled(&s->tmdA1, s->da1, H1 / 64, mb128, nb))) return rc2;
         if ((rc2 = make_map_tiled(&s->tmdA2, s->da2, H2 / 64, mb128, nb))) return rc2;
+        if ((rc2 = make_map(&s->tmX64, s->xs, 2 * D_IN_PAD, n_local, 1, 64))) return rc2;
+        if ((rc2 = make_map(&s->tmW2c64, s->w2c, 2 * H1, H2, nb, 64))) return rc2;
         return PMP_OK;
     }
     PMP_CUDA(cudaMalloc((void**)&s->w1, (size_t)nb * H1 * 3 * D_IN_PAD * 2));
@@ -1245,6 +1333,11 @@ int pmp_fc_loglik(pmp_ctx* c) {
                  (double)c->cfg.alpha * sqrt((double)(c->cfg.tree == PMP_TREE_FLAT ? 1 : c->cfg.depth)) <= 1e-3;
     if (const char* m = getenv("PMP_FC_MODE")) { if (!strcmp(m, "x3")) delta = false; else if (!strcmp(m, "delta") && s->version == 2 && s->nb <= L4_NB) delta = true; }
     if (delta) {
+        // TMA multicast over clusters of two CTA pairs (layers 1, 2): built, parity-green, and SLOWER — opt-in with PMP_FC_MCAST=1.  ncu (r2q): the bytes an
+        // SM ingests through the crossbar are unchanged (l1tex__m_xbar2l1tex_read_bytes 3.74 GB vs 3.71 GB per 8 nodes: multicast saves L2 reads, not SM
+        // ingest, and SM ingest is the bound), only 33 four-CTA clusters are co-resident (132 SMs), and the relay hop + joint stage release cost
+        // latency: 12.3 ms against 7.1 ms per P=64 sweep.
+        const bool mcast = getenv("PMP_FC_MCAST") && atoi(getenv("PMP_FC_MCAST")) == 1 && c->sm_count % 4 == 0;
         const float* th0 = c->d_props;                               // node 0 = the current state
         const int mb128 = (M + 127) / 128;
         long long t;
@@ -1273,13 +1366,15 @@ int pmp_fc_loglik(pmp_ctx* c) {
             PMP_CUDA(cudaGetLastError());
             Gemm3Args g1{}; g1.M = M; g1.nb = nb; g1.n_total = H1; g1.mb128 = mb128; g1.nk_a = D_IN_PAD / BK; g1.nk_total = D_IN_PAD / BK; g1.a_rowmajor = 1;
             g1.dbias = s->dbias; g1.dbias_stride = bias_stride; g1.t0h = s->t1; g1.out = s->da1;
-            if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6>(c, s->tmX, s->tmX, s->tmdW1, g1))) return rc;
+            if (mcast) { if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 1>(c, s->tmX, s->tmX64, s->tmdW1, g1))) return rc; }
+            else if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 0>(c, s->tmX, s->tmX, s->tmdW1, g1))) return rc;
             Gemm3Args g2{}; g2.M = M; g2.nb = nb; g2.n_total = H2; g2.mb128 = mb128; g2.nk_a = H1 / BK; g2.nk_total = 2 * H1 / BK; g2.a_rowmajor = 0;
             g2.dbias = s->dbias + H1; g2.dbias_stride = bias_stride; g2.t0h = s->t2; g2.out = s->da2;
-            if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6>(c, s->tmdA1, s->tmA2b, s->tmW2c, g2))) return rc;
+            if (mcast) { if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 2>(c, s->tmdA1, s->tmA2b, s->tmW2c64, g2))) return rc; }
+            else if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 0>(c, s->tmdA1, s->tmA2b, s->tmW2c, g2))) return rc;
             Gemm3Args g3{}; g3.M = M; g3.nb = nb; g3.n_total = H3; g3.mb128 = mb128; g3.nk_a = H2 / BK; g3.nk_total = 2 * H2 / BK; g3.a_rowmajor = 0;
             g3.dbias = s->dbias + H1 + H2; g3.dbias_stride = bias_stride; g3.t0f = s->t3; g3.theta = th; g3.theta_stride = THETA_DIM; g3.labels = s->labels; g3.loss = s->loss + p0;
-            if ((rc = launch_gemm3<128, EPI3_L4_NLL, 6>(c, s->tmdA2, s->tmA3b, s->tmW3c, g3))) return rc;
+            if ((rc = launch_gemm3<128, EPI3_L4_NLL, 6, 0>(c, s->tmdA2, s->tmA3b, s->tmW3c, g3))) return rc;
         }
     }
     for (int p0 = 0; p0 < P && !delta; p0 += s->nb) {
