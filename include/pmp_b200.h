@@ -63,7 +63,8 @@ typedef enum pmp_target {
     PMP_TARGET_FC = 4,           /* -CE(MLP 784-512-256-128-10)/loss_div (PMP_FC.py:21-44); needs set_data_fc */
     PMP_TARGET_EXTERNAL = 5,     /* log-targets supplied with pmp_write_logtarget (arbitrary loss(net) callables) */
     PMP_TARGET_GLM_LOGISTIC = 6, /* sum_i log sigmoid(s_i x_i.theta), s_i = 2 y_i - 1, theta in R^d; needs pmp_set_data_glm */
-    PMP_TARGET_GLM_GAUSS = 7     /* y_i ~ N(x_i.theta[0:d], theta[d]^2): d coefficients + sigma, dim = d + 1 (lb.py:100-108 with a d-vector covariate) */
+    PMP_TARGET_GLM_GAUSS = 7,    /* y_i ~ N(x_i.theta[0:d], theta[d]^2): d coefficients + sigma, dim = d + 1 (lb.py:100-108 with a d-vector covariate) */
+    PMP_TARGET_CNN = 8           /* -CE(conv 1->10 5x5, pool, conv 10->20 3x3, 2000-500-10)/loss_div (PMP_CNN.py:22-52); needs pmp_set_data_cnn */
 } pmp_target;
 
 /* Acceptance rule: how the P log-targets become log-weights. */
@@ -220,6 +221,12 @@ int pmp_set_data_fc(pmp_ctx* ctx, const float* X, const int64_t* labels, int64_t
  * for LOGISTIC, responses for GAUSS).  The P x n sweep is ONE tcgen05 GEMM [n, d] x [d, P] with a fused softplus / square epilogue
  * and a warp-shuffle per-node reduction; shards must start at multiples of 32 rows. */
 int pmp_set_data_glm(pmp_ctx* ctx, const float* X, const float* y, int64_t n_local, int64_t n_offset, int64_t n_global, int d);
+
+/* ---- CNN model (complex_nets/Mnist/CNN/PMP_CNN.py:22-44; the same Model in MP_CNN.py, MH_CNN.py): X [n,784] float32 row-major (28x28 images),
+ * labels int64; theta layout = torch parameter order conv1.weight[10,1,5,5], conv1.bias[10], conv2.weight[20,10,3,3], conv2.bias[20],
+ * fc1.weight[500,2000], fc1.bias[500], fc2.weight[10,500], fc2.bias[10] (1 007 590 floats, CNN_model.pkl).  Replaces the loop
+ * `weights[all] = exp(-loss(proposal_nets[all]))` PMP_CNN.py:119-120 for PMP_TARGET_CNN; sharded by rows like the FC target. */
+int pmp_set_data_cnn(pmp_ctx* ctx, const float* X, const int64_t* labels, int64_t n_local, int64_t n_offset, int64_t n_global);
 
 #ifdef __cplusplus
 }

@@ -499,6 +499,82 @@ def fc_loss_torch32(X, y, theta, div=10.0):
         return float(torch.nn.CrossEntropyLoss()(x, torch.from_numpy(np.asarray(y, dtype=np.int64))) / div)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# CNN model (complex_nets/Mnist/CNN/PMP_CNN.py:22-52): conv1(1->10, 5x5) ReLU maxpool2 conv2(10->20, 3x3) ReLU fc1(2000->500) ReLU fc2(500->10)
+# log_softmax; loss = CrossEntropy(mean)(log-probabilities, y) / 10 (the cross-entropy applies its own log-softmax on top: a no-op in exact arithmetic)
+CNN_SHAPES = [(10, 1, 5, 5), (10,), (20, 10, 3, 3), (20,), (500, 2000), (500,), (10, 500), (10,)]   # torch parameter order
+CNN_DIM = sum(int(np.prod(s)) for s in CNN_SHAPES)
+
+
+def cnn_unpack(theta):
+    out, off = [], 0
+    for s in CNN_SHAPES:
+        k = int(np.prod(s))
+        out.append(np.asarray(theta[off:off + k]).reshape(s))
+        off += k
+    return out
+
+
+def cnn_init_theta(seed=0):
+    """torch's default init scale (uniform +-1/sqrt(fan_in)) from a seeded generator: a deterministic stand-in for CNN_model.pkl."""
+    rng = np.random.default_rng(seed)
+    fan = [25, 25, 90, 90, 2000, 2000, 500, 500]
+    return np.concatenate([rng.uniform(-1, 1, size=int(np.prod(s))) / math.sqrt(f) for s, f in zip(CNN_SHAPES, fan)]).astype(np.float32)
+
+
+def cnn_logits_numpy(X, theta, dtype=np.float64):
+    """The forward pass PMP_CNN.py:32-42 written out with explicit loops over the filter taps (small n only)."""
+    W1, b1, W2, b2, F1, c1, F2, c2 = [a.astype(dtype) for a in cnn_unpack(theta)]
+    x = np.asarray(X, dtype=dtype).reshape(-1, 28, 28)
+    n = len(x)
+    t = np.zeros((n, 10, 24, 24), dtype)
+    for ky in range(5):
+        for kx in range(5):
+            t += W1[None, :, 0, ky, kx, None, None] * x[:, None, ky:ky + 24, kx:kx + 24]
+    t = np.maximum(t + b1[None, :, None, None], 0)
+    p = t.reshape(n, 10, 12, 2, 12, 2).max(axis=(3, 5))
+    u = np.zeros((n, 20, 10, 10), dtype)
+    for c in range(10):
+        for ky in range(3):
+            for kx in range(3):
+                u += W2[None, :, c, ky, kx, None, None] * p[:, None, c, ky:ky + 10, kx:kx + 10]
+    u = np.maximum(u + b2[None, :, None, None], 0).reshape(n, 2000)
+    h = np.maximum(u @ F1.T + c1, 0)
+    return h @ F2.T + c2
+
+
+def cnn_mean_ce_f64(X, y, theta, chunk=4096):
+    """Ground truth: forward pass + CrossEntropyLoss(mean) in binary64 from the float32 inputs (torch float64 convolutions, chunked over rows;
+    pinned against cnn_logits_numpy in tests/test_cpu_cnn.py)."""
+    import torch
+    import torch.nn.functional as F
+    W1, b1, W2, b2, F1, c1, F2, c2 = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)) for a in cnn_unpack(theta)]
+    y = np.asarray(y)
+    tot = 0.0
+    with torch.no_grad():
+        for i in range(0, len(y), chunk):
+            x = torch.from_numpy(np.ascontiguousarray(X[i:i + chunk], dtype=np.float64)).view(-1, 1, 28, 28)
+            o = F.max_pool2d(F.relu(F.conv2d(x, W1, b1)), 2, 2)
+            o = F.relu(F.conv2d(o, W2, b2)).reshape(len(x), -1)
+            z = F.linear(F.relu(F.linear(o, F1, c1)), F2, c2)
+            ls = F.log_softmax(z, dim=1)
+            tot += float(-ls[torch.arange(len(x)), torch.from_numpy(y[i:i + chunk].astype(np.int64))].sum())
+    return tot / len(y)
+
+
+def cnn_loss_torch32(X, y, theta, div=10.0):
+    """loss(net) exactly as the reference evaluates it (PMP_CNN.py:48-52): torch float32, CrossEntropyLoss()(log_softmax(net(X)), y) / 10."""
+    import torch
+    import torch.nn.functional as F
+    W1, b1, W2, b2, F1, c1, F2, c2 = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)) for a in cnn_unpack(theta)]
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).view(-1, 1, 28, 28)
+        o = F.max_pool2d(F.relu(F.conv2d(x, W1, b1)), 2, 2)
+        o = F.relu(F.conv2d(o, W2, b2)).view(len(x), -1)
+        z = F.log_softmax(F.linear(F.relu(F.linear(o, F1, c1)), F2, c2), dim=1)
+        return float(torch.nn.CrossEntropyLoss()(z, torch.from_numpy(np.asarray(y, dtype=np.int64))) / div)
+
+
 # ---- d-dimensional GLM heads (extension of the simple-net model, SURVEY 8f rank 1; no reference counterpart: plain binary64) ----
 def loglik_glm_f64(X, y, thetas, kind, scale=1.0):
     """kind 'logistic': sum_i log sigmoid(s_i x_i.theta), s_i = 2 y_i - 1.  kind 'gauss': theta = (coefficients, sigma),

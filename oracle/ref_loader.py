@@ -94,3 +94,25 @@ def load_fc(kind, X, y, device="cpu"):
         src += "".join(lines[a:b]) + "\n"
     exec(compile(src, path, "exec"), ns)
     return ns
+
+
+def load_cnn(kind, X, y, device="cpu"):
+    """complex_nets/Mnist/CNN/{MH,MP,PMP}_CNN.py: Model (conv 1->10 5x5, pool, conv 10->20 3x3, 2000-500-10, log_softmax), loss and the
+    optimizer class, with the MNIST download replaced by injected globals X [n,1,28,28] float32, y [n] int64."""
+    import copy
+    import math
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from torch import nn
+    path = os.path.join(REF, "complex_nets/Mnist/CNN/%s_CNN.py" % kind)
+    with open(path, encoding="utf-8-sig") as f:
+        lines = f.readlines()
+    ns = {"torch": torch, "F": F, "nn": nn, "copy": copy, "math": math, "np": np, "tqdm": lambda it: it, "device": device,
+          "X": X, "y": y, "x_test": X[:16], "y_test": y[:16], "batch_size": int(X.shape[0]), "N": 7, "alpha": 1e-4}
+    ranges = {"PMP": [(21, 52), (86, 194)], "MP": [(19, 44), (75, 80), (82, 169)], "MH": [(17, 42), (73, 78), (79, 141)]}[kind]
+    src = ""
+    for a, b in ranges:
+        src += "".join(lines[a:b]) + "\n"
+    exec(compile(src, path, "exec"), ns)
+    return ns

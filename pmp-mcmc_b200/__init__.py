@@ -5,6 +5,7 @@ prefetch-tree expansion + multi-proposal acceptance) behind the reference's own 
     samplers    lb.py names: BayesNet, MetropolisOptimizer, GMOptimizer, preMOptimizer, GMpreOptimizerV2
     analytic    error.py / com_dim.py names: SP, MP, PSP, PMP, normal, banana_distribution
     fc          PMP_FC.py / MP_FC.py / MH_FC.py names: Model, loss, MetropolisOptimizer, MPOptimizer, PMPOptimizer
+    cnn         PMP_CNN.py / MP_CNN.py / MH_CNN.py names (Model, loss, the three optimizers) on the device CNN sweep
     nets        the same three network samplers around an arbitrary loss(net) callable (CNN / LSTM scripts)
     cuda_programs  the .cu experiment programs' main() (time analysis, convergence, ESS dumps) on the device-resident chain
     sinks       trace files in the reference's text formats + the readers its notebooks use

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(CSRC, "libpmp_b200.so")
 
 # enums of include/pmp_b200.h
 TREE_FLAT, TREE_BINARY, TREE_BARY = 0, 1, 2
-TARGET_LINEAR_GAUSS, TARGET_NORMAL1D, TARGET_BANANA, TARGET_STDNORMAL, TARGET_FC, TARGET_EXTERNAL, TARGET_GLM_LOGISTIC, TARGET_GLM_GAUSS = range(8)
+TARGET_LINEAR_GAUSS, TARGET_NORMAL1D, TARGET_BANANA, TARGET_STDNORMAL, TARGET_FC, TARGET_EXTERNAL, TARGET_GLM_LOGISTIC, TARGET_GLM_GAUSS, TARGET_CNN = range(9)
 ALGO_MH, ALGO_BARKER, ALGO_MP, ALGO_PSP, ALGO_PMP, ALGO_TABLE = range(6)
 DRAW_PYTHON, DRAW_CUDA, DRAW_SINGLE = range(3)
 FLAG_QUIRK_LEVEL_MOD, FLAG_QUIRK_TABLE_CONST, FLAG_STANDARDIZE, FLAG_KERNEL_MEAN, FLAG_NO_KERNEL_TERM, FLAG_UNIFORM_PROPOSAL = 1, 2, 4, 8, 16, 32
@@ -26,7 +26,7 @@ EXPORTS = [
     "pmp_run_timed", "pmp_launch_count", "pmp_fp32_peak", "pmp_l2_flush", "pmp_chains_create", "pmp_chains_run",
     "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
     "pmp_stream_normals", "pmp_time_sweep", "pmp_share_data", "pmp_run_multi", "pmp_run_multi_timed",
-    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach", "pmp_trace_diagnostics", "pmp_set_data_glm",
+    "pmp_peer_exchange_handle", "pmp_peer_exchange_attach", "pmp_trace_diagnostics", "pmp_set_data_glm", "pmp_set_data_cnn",
 ]
 
 
@@ -105,6 +105,7 @@ def load():
     L.pmp_chains_read_samples.argtypes = [vp, vp, i64]
     L.pmp_chains_run_timed.argtypes = [vp, i64, i32, ctypes.POINTER(ctypes.c_float)]
     L.pmp_set_data_fc.argtypes = [vp, vp, vp, i64, i64, i64]
+    L.pmp_set_data_cnn.argtypes = [vp, vp, vp, i64, i64, i64]
     L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_share_data.argtypes = [vp, vp]
@@ -387,6 +388,13 @@ class Context:
         if X.ndim != 2 or len(X) != len(y):
             raise ValueError("X must be [n, d] and y [n]")
         self._chk(self.L.pmp_set_data_glm(self.h, _ptr(X), _ptr(y), len(y), n_offset, len(y) if n_global is None else n_global, X.shape[1]))
+
+    def set_data_cnn(self, X, labels, n_offset=0, n_global=None):
+        X = np.ascontiguousarray(X, dtype=np.float32).reshape(len(labels), -1)
+        if X.shape[1] != 784:
+            raise ValueError("the CNN target takes 28x28 images")
+        lab = np.ascontiguousarray(labels, dtype=np.int64)
+        self._chk(self.L.pmp_set_data_cnn(self.h, _ptr(X), _ptr(lab), len(lab), n_offset, len(lab) if n_global is None else n_global))
 
     def set_data_fc(self, X, labels, n_offset=0, n_global=None):
         X = np.ascontiguousarray(X, dtype=np.float32).reshape(len(labels), -1)

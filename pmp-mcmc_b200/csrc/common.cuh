@@ -124,6 +124,7 @@ struct pmp_ctx {
     // FC model, GLM heads
     void* fc = nullptr;
     void* glm = nullptr;
+    void* cnn = nullptr;
 
     // peer-memory exchange of the per-node sums (world > 1, pmp_peer_exchange_*): own buffer + the peers' buffers mapped with CUDA IPC
     unsigned long long* d_xchg = nullptr;

@@ -99,6 +99,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ float2 ffma2f(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) { return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16); }
 
 struct GemmArgs {
@@ -270,7 +275,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1, EPI2_GLM = 2 };
+enum { EPI2_RELU_SPLIT = 0, EPI2_L4_NLL = 1, EPI2_GLM = 2, EPI2_HEAD = 3 };
+constexpr int HEAD_PITCH = 12;                                    // floats per row of the partial-logit output (10 classes + 2 pad)
 enum { GLM_LOGISTIC = 0, GLM_GAUSS = 1 };
 constexpr int GLM_FX_SHIFT = 24;                                 // fixed-point format of the per-node sums of the GLM heads
 constexpr int GEMM2_EPI_WARPS = 8;                               // two warps per TMEM lane quarter, each takes half of the tile's columns
@@ -300,6 +306,12 @@ struct Gemm2Args {
     // RELU_SPLIT, base pass of the delta formulation (node 0 only): also keep the PRE-activations acc + bias, row-major [rows, n_total]
     __half* t_out16;          // binary16: enough to locate the ReLU kinks (layers 1, 2)
     float* t_out32;           // float32: layer 3 (its activations feed the float32 last layer)
+    // HEAD (CNN: the 500 -> 10 layer folded into the epilogue of the 2000 -> 500 layer, PMP_CNN.py:29-30,41-44): relu(acc + bias) . W_head^T over this
+    // tile's BN columns, in float32 on the CUDA cores; the per-tile partial logits go to head_part [nb][n_total / BN][M][HEAD_PITCH] and a small kernel
+    // adds the column blocks in a fixed order (cnn_head_nll_kernel).  head_w = the first node's [10, head_k] row-major weight (node stride theta_stride).
+    const float* head_w;
+    int head_k;               // real width of the hidden layer (columns >= head_k are padding: zero weights)
+    float* head_part;
 };
 
 template <int BN, int EPI, int NSTAGE>
@@ -316,7 +328,9 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_w4[EPI == EPI2_L4_NLL ? H3 * 12 : 4];
     __shared__ float s_b3[EPI == EPI2_L4_NLL ? H3 : 1], s_b4[EPI == EPI2_L4_NLL ? NCLS_PAD : 1];
-    __shared__ float s_z[EPI == EPI2_L4_NLL ? BM * (NCLS + 1) : 1];     // partial logits of the upper column half, [row][11]
+    __shared__ float s_z[(EPI == EPI2_L4_NLL || EPI == EPI2_HEAD) ? BM * (NCLS + 1) : 1];     // partial logits of the upper column half, [row][11]
+    __shared__ __align__(16) float s_wh[EPI == EPI2_HEAD ? BN * 12 : 4];   // HEAD: this tile's BN rows of the transposed head weight, 12-float rows
+    __shared__ float s_bh[EPI == EPI2_HEAD ? BN : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -413,10 +427,58 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (et < NCLS) s_b4[et] = __ldg(th + OFF_B4 + et);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
+            if (EPI == EPI2_HEAD) {                              // this node's head weights for the tile's BN hidden units -> shared memory
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float* hw = g.head_w + (long long)batch * g.theta_stride;
+                for (int i = et; i < NCLS * BN; i += 32 * GEMM2_EPI_WARPS) {
+                    const int c = i / BN, jj = i - c * BN, col = n_blk * BN + jj;
+                    s_wh[jj * 12 + c] = col < g.head_k ? __ldg(hw + (long long)c * g.head_k + col) : 0.f;
+                }
+                for (int jj = et; jj < BN; jj += 32 * GEMM2_EPI_WARPS) { s_wh[jj * 12 + 10] = 0.f; s_wh[jj * 12 + 11] = 0.f; s_bh[jj] = __ldg(g.bias + (long long)batch * g.bias_stride + n_blk * BN + jj); }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(&tfull_bar[acc], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * CH);
-            if (EPI == EPI2_RELU_SPLIT) {
+            if (EPI == EPI2_HEAD) {
+                float2 z2[NCLS / 2];
+#pragma unroll
+                for (int c = 0; c < NCLS / 2; ++c) z2[c] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                for (int cc = 0; cc < CH / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int jj = chalf * CH + cc * 32 + i;
+                        const float a = fmaxf(__uint_as_float(v[i]) + s_bh[jj], 0.f);
+                        const float4 w0 = *reinterpret_cast<const float4*>(&s_wh[jj * 12]);
+                        const float4 w1 = *reinterpret_cast<const float4*>(&s_wh[jj * 12 + 4]);
+                        const float2 w2 = *reinterpret_cast<const float2*>(&s_wh[jj * 12 + 8]);
+                        const float2 aa = make_float2(a, a);
+                        z2[0] = ffma2f(aa, make_float2(w0.x, w0.y), z2[0]); z2[1] = ffma2f(aa, make_float2(w0.z, w0.w), z2[1]);
+                        z2[2] = ffma2f(aa, make_float2(w1.x, w1.y), z2[2]); z2[3] = ffma2f(aa, make_float2(w1.z, w1.w), z2[3]);
+                        z2[4] = ffma2f(aa, w2, z2[4]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? lempty1 : lempty0);
+                if (chalf == 1) {
+#pragma unroll
+                    for (int c = 0; c < NCLS / 2; ++c) { s_z[lrow * (NCLS + 1) + 2 * c] = z2[c].x; s_z[lrow * (NCLS + 1) + 2 * c + 1] = z2[c].y; }
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (chalf == 0 && row < g.M) {                   // lower half + upper half, in this order: the sum is a function of the tile alone
+                    float* o = g.head_part + (((long long)batch * nblk_n + n_blk) * g.M + row) * HEAD_PITCH;
+                    float z[12];
+#pragma unroll
+                    for (int c = 0; c < NCLS / 2; ++c) { z[2 * c] = z2[c].x + s_z[lrow * (NCLS + 1) + 2 * c]; z[2 * c + 1] = z2[c].y + s_z[lrow * (NCLS + 1) + 2 * c + 1]; }
+                    z[10] = 0.f; z[11] = 0.f;
+#pragma unroll
+                    for (int q4 = 0; q4 < 3; ++q4) reinterpret_cast<float4*>(o)[q4] = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+                }
+            } else if (EPI == EPI2_RELU_SPLIT) {
                 const float* bias = g.bias + (long long)batch * g.bias_stride + n_blk * BN + chalf * CH;
                 // tile-major output: [batch][128-row block][k-tile of 64 columns (h tiles, then l tiles)][row][64]
                 const int kt_half = g.n_total / 64;
@@ -591,11 +653,6 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // Same skeleton as fc_gemm2_kernel: CTA pairs (cta_group::2), persistent, node-fastest tile order, two TMEM accumulator stages.
 enum { EPI3_DELTA_RELU = 0, EPI3_L4_NLL = 1 };
 constexpr int L4_NB = 8;                                          // nodes per launch whose last layer fits the L4_NLL kernel's shared memory
-__device__ __forceinline__ float2 ffma2f(float2 a, float2 b, float2 c) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2*>(&rd);
-}
 
 struct Gemm3Args {
     int M, nb, n_total, mb128;
@@ -1531,3 +1588,5 @@ int pmp_glm_loglik(pmp_ctx* c) {
 }
 
 }  // extern "C"
+
+#include "cnn_sweep.cuh"

@@ -16,6 +16,7 @@
 #include "chain_persistent_multi.cuh"
 
 extern "C" int pmp_fc_loglik(pmp_ctx* c);   // fc_sweep.cu
+extern "C" int pmp_cnn_loglik(pmp_ctx* c);  // cnn_sweep.cuh (compiled with fc_sweep.cu)
 extern "C" int pmp_glm_loglik(pmp_ctx* c);  // fc_sweep.cu
 extern "C" int pmp_glm_destroy(pmp_ctx* c);
 #include "common.cuh"
@@ -284,6 +285,7 @@ static int enqueue_iteration(pmp_ctx* c, cudaEvent_t sweep_begin, cudaEvent_t sw
         set_error("pmp_run: target %d needs host-driven log-targets (use pmp_propose / pmp_write_logtarget / pmp_accept)", c->cfg.target);
         return PMP_ERR_UNSUPPORTED;
     }
+    if (c->cfg.target == PMP_TARGET_CNN && (rc = pmp_cnn_loglik(c))) return rc;   // direct convolutions + GEMM with the fused head, same contract as the FC target
     if (c->cfg.target == PMP_TARGET_FC && (rc = pmp_fc_loglik(c))) return rc;     // GEMM chain + all-reduce of the integer loss sums, all on the ctx stream
     if ((c->cfg.target == PMP_TARGET_GLM_LOGISTIC || c->cfg.target == PMP_TARGET_GLM_GAUSS) && (rc = pmp_glm_loglik(c))) return rc;
     if ((rc = launch_accept(c, 0, 0, 1, nullptr))) return rc;
@@ -404,6 +406,7 @@ int pmp_create(pmp_ctx** out, int device, int world_size, int rank, const void* 
 }
 
 int pmp_fc_destroy(pmp_ctx* ctx);       // fc_sweep.cu
+int pmp_cnn_destroy(pmp_ctx* ctx);      // cnn_sweep.cuh
 int pmp_chains_destroy(pmp_ctx* ctx);   // chains.cu
 
 int pmp_destroy(pmp_ctx* c) {
@@ -412,6 +415,7 @@ int pmp_destroy(pmp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     drop_graph(c);
     pmp_fc_destroy(c);
+    pmp_cnn_destroy(c);
     pmp_glm_destroy(c);
     pmp_chains_destroy(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
@@ -452,7 +456,7 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY || cfg->b >= 1, "b=%d must be >= 1", cfg->b);
     PMP_REQUIRE(P >= 1 && P <= MAX_NODES, "P=%lld nodes out of range [1,%d]", P, MAX_NODES);
     PMP_REQUIRE(cfg->dim >= 1, "dim must be >= 1");
-    PMP_REQUIRE(cfg->target >= 0 && cfg->target <= PMP_TARGET_GLM_GAUSS, "unknown target %d", cfg->target);
+    PMP_REQUIRE(cfg->target >= 0 && cfg->target <= PMP_TARGET_CNN, "unknown target %d", cfg->target);
     PMP_REQUIRE(cfg->algo >= 0 && cfg->algo <= PMP_ALGO_TABLE, "unknown algo %d", cfg->algo);
     PMP_REQUIRE(cfg->draw >= 0 && cfg->draw <= PMP_DRAW_SINGLE, "unknown draw rule %d", cfg->draw);
     if (cfg->target == PMP_TARGET_LINEAR_GAUSS) PMP_REQUIRE(cfg->dim == 3, "linear-Gaussian target has dim 3 (b0,b1,sigma), got %d", cfg->dim);
@@ -461,7 +465,7 @@ int pmp_configure(pmp_ctx* c, const pmp_config* cfg) {
     if (cfg->algo == PMP_ALGO_MH || cfg->algo == PMP_ALGO_BARKER) PMP_REQUIRE(P == 2, "MH/BARKER need P == 2 (FLAT, b=2), got %lld", P);
     if (cfg->algo == PMP_ALGO_PSP) PMP_REQUIRE(cfg->tree == PMP_TREE_BINARY, "PSP needs the BINARY tree");
     if (cfg->algo == PMP_ALGO_PMP) PMP_REQUIRE(cfg->tree == PMP_TREE_BARY || cfg->tree == PMP_TREE_BINARY, "PMP needs a BARY/BINARY tree");
-    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC && cfg->target != PMP_TARGET_EXTERNAL && cfg->target != PMP_TARGET_GLM_LOGISTIC && cfg->target != PMP_TARGET_GLM_GAUSS)
+    if (cfg->algo == PMP_ALGO_MP && !(cfg->flags & PMP_FLAG_NO_KERNEL_TERM) && cfg->target != PMP_TARGET_FC && cfg->target != PMP_TARGET_CNN && cfg->target != PMP_TARGET_EXTERNAL && cfg->target != PMP_TARGET_GLM_LOGISTIC && cfg->target != PMP_TARGET_GLM_GAUSS)
         PMP_REQUIRE(cfg->dim <= KDIM_MAX, "in-kernel MP kernel term supports dim <= %d for this target", KDIM_MAX);
     PMP_REQUIRE(cfg->scale != 0.f && cfg->kernel_sigma > 0.f, "scale must be non-zero and kernel_sigma > 0");
 
@@ -618,6 +622,8 @@ int pmp_loglik(pmp_ctx* c, double* out_host) {
         if ((rc = launch_accept(c, 1, 1, 0, nullptr))) return rc;
     } else if (c->cfg.target == PMP_TARGET_FC) {
         if ((rc = pmp_fc_loglik(c))) return rc;
+    } else if (c->cfg.target == PMP_TARGET_CNN) {
+        if ((rc = pmp_cnn_loglik(c))) return rc;
     } else if (c->cfg.target == PMP_TARGET_GLM_LOGISTIC || c->cfg.target == PMP_TARGET_GLM_GAUSS) {
         if ((rc = pmp_glm_loglik(c))) return rc;
     } else if (c->cfg.target == PMP_TARGET_EXTERNAL) {
@@ -870,7 +876,7 @@ static int run_impl(pmp_ctx* c, int64_t iters) {
     }
     if ((rc = ensure_comm(c))) return rc;             // stepwise loop with NCCL between kernels: the communicator must exist before any stream capture
     int64_t done = 0;
-    if (GI > 1 && iters >= GI && c->cfg.target != PMP_TARGET_FC && c->cfg.target != PMP_TARGET_GLM_LOGISTIC && c->cfg.target != PMP_TARGET_GLM_GAUSS) {     // FC iterations are milliseconds of GEMMs: nothing to gain from a graph
+    if (GI > 1 && iters >= GI && c->cfg.target != PMP_TARGET_FC && c->cfg.target != PMP_TARGET_CNN && c->cfg.target != PMP_TARGET_GLM_LOGISTIC && c->cfg.target != PMP_TARGET_GLM_GAUSS) {     // FC iterations are milliseconds of GEMMs: nothing to gain from a graph
         if (!c->graph_exec || c->graph_iters != GI) {
             drop_graph(c);
             cudaGraph_t graph;

@@ -61,8 +61,8 @@ def flatten(net):
     return torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu().numpy().astype(np.float32)
 
 
-def unflatten(theta, like=None):
-    net = Model() if like is None else copy.deepcopy(like)
+def unflatten(theta, like=None, model=None):
+    net = (model or Model)() if like is None else copy.deepcopy(like)
     off = 0
     with torch.no_grad():
         for p in net.parameters():
@@ -91,6 +91,11 @@ def loss(net):
 
 class _FCBase:
     tree, algo, flags, draw, scale, temperature = L.TREE_FLAT, L.ALGO_MP, 0, L.DRAW_SINGLE, 10.0, 1.0
+    _target, _dim = L.TARGET_FC, FC_DIM          # cnn.py reuses these samplers with the CNN target (the reference's optimizer classes are the same code)
+
+    @staticmethod
+    def _context():
+        return _ctx
 
     def __init__(self, net, alpha, seed=0):
         self.net = net
@@ -120,9 +125,12 @@ class _FCBase:
 
     def _configure(self):
         tree, b, depth = self._shape()
-        _ctx.configure(tree, b=b, depth=depth, dim=FC_DIM, target=L.TARGET_FC, algo=self.algo, draw=self.draw, flags=self.flags,
-                       alpha=float(self.alpha), scale=self.scale, kernel_sigma=float(self.sigma), mh_temperature=self.temperature)
-        return _ctx
+        ctx = self._context()
+        if ctx is None:
+            raise RuntimeError("set_data(X, y) first")
+        ctx.configure(tree, b=b, depth=depth, dim=self._dim, target=self._target, algo=self.algo, draw=self.draw, flags=self.flags,
+                      alpha=float(self.alpha), scale=self.scale, kernel_sigma=float(self.sigma), mh_temperature=self.temperature)
+        return ctx
 
     def _step_device(self, uniforms=None):
         """propose → sweep → accept on the device; returns (accepted index, mean CE of every node)."""
