@@ -343,6 +343,40 @@ def extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps):
                          "note": "ALGORITHMIC flops 2*566528*n per node; `achieved` times the P-node sweep (pmp_loglik) alone, `achieved_whole_iteration` one full pmp_run iteration (propose + sweep + all-reduce + acceptance)"}}
 
 
+def extra_cnn(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps, fp32_peak):
+    """the CNN of complex_nets/Mnist/CNN/PMP_CNN.py:22-52 on synthetic MNIST-shaped rows, n = 60 000 sharded over the ranks, P = 64 nodes
+    (binary prefetch tree D = 6; the reference script runs N + 1 = 8), theta0 = CNN_model.pkl (tests/golden/cnn_theta0.npy).  Two kernels carry the sweep:
+    the float32 direct convolutions on the CUDA cores (648 000 flop per node and row) and the tcgen05 fc1 GEMM with the fused head (2 010 000 flop)."""
+    n, depth, dim = FC_N, 6, 1007590
+    rng = np.random.default_rng(0)
+    lo, hi = pdist.shard_bounds(n, world, rank, align=128)
+    X = rng.standard_normal((n, 784), dtype=np.float32)
+    yl = rng.integers(0, 10, size=n).astype(np.int64)
+    theta0 = np.load(os.path.join(ROOT, "tests", "golden", "cnn_theta0.npy"))
+    ctx.configure(L.TREE_BINARY, depth=depth, dim=dim, target=L.TARGET_CNN, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+    ctx.set_data_cnn(X[lo:hi], yl[lo:hi], n_offset=lo, n_global=n)
+    del X
+    ctx.set_state(theta0); ctx.seed(1, 0)
+    ctx.trace_config(2 + steps, L.TRACE_NEXT)
+    ctx.run(1)
+    ms = [max_over_ranks(ctx.run_timed(1)[0]) for _ in range(steps)]
+    nxt = ctx.read_trace()["next"]
+    ctx.propose(); ctx.sync()
+    t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = max_over_ranks(time.perf_counter() - t0)
+    lt = ctx.loglik()
+    P = 1 << depth
+    it_s = float(np.mean(ms)) * 1e-3
+    conv, dense = 2.0 * 324000 * n * P, 2.0 * 1005000 * n * P
+    return {"workload": "CNN conv(1->10,5x5)-pool-conv(10->20,3x3)-2000-500-10 (PMP_CNN.py:22-52), n=%d rows sharded over %d rank(s), P=%d nodes (binary tree D=%d), alpha=1e-4, theta0=CNN_model.pkl" % (n, world, P, depth),
+            "value": P / it_s, "unit": UNIT, "iters_per_sec": 1.0 / it_s, "ms_per_iter": it_s * 1e3, "sweep_ms": sweep_s * 1e3, "ms_per_node": sweep_s * 1e3 / P,
+            "accepted": [int(v) for v in nxt], "logtarget_range": [float(lt.min()), float(lt.max())],
+            "roofline": {"bound": "fp32 (convolutions) + tensor (fc1)", "achieved": (conv + dense) / sweep_s / 1e12, "unit": "TFLOP/s",
+                         "lower_bound_ms_per_node": 1e3 * (conv / P / (fp32_peak * 1e12 * world) + dense / P / (peaks.get("bf16_tflops_sustained", 1383.9) * 1e12 * world)),
+                         "frac": (conv / (fp32_peak * 1e12 * world) + dense / (peaks.get("bf16_tflops_sustained", 1383.9) * 1e12 * world)) / sweep_s,
+                         "note": "ALGORITHMIC flops; the two kernels run back to back, so the bound is the SUM of the convolutions at the measured FP32 peak and the dense "
+                                 "layers at the sustained bf16 peak; frac = that bound / measured sweep time (fc1 executes 3x its algorithmic flops: bf16x3)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -352,7 +386,7 @@ def main():
     ap.add_argument("--iters-per-step", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--weak", action="store_true", help="n = 100000 per GPU instead of 100000 in total")
     ap.add_argument("--chains", type=int, default=CHAINS, help="independent chains of the co_scheduled block (pmp_run_multi)")
-    ap.add_argument("--skip", default="", help="comma list of extra blocks to skip: co,n500,pmp,analytic,fc,cpu")
+    ap.add_argument("--skip", default="", help="comma list of extra blocks to skip: co,n500,pmp,analytic,fc,cnn,cpu")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -536,6 +570,8 @@ def main():
             extras["analytic"] = extra_analytic(pm, L, local, hbm_peak)
     if "fc" not in skip:
         extras["fc"] = extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, 2)
+    if "cnn" not in skip:
+        extras["cnn"] = extra_cnn(L, pdist, ctx, world, rank, max_over_ranks, peaks, 2, peak)
 
     if rank == 0:
         cpu = None

@@ -25,9 +25,13 @@ constexpr long long CNN_DIM = 1007590;
 constexpr long long C_OFF_W1 = 0, C_OFF_B1 = 250, C_OFF_W2 = 260, C_OFF_B2 = 2060, C_OFF_FW1 = 2080, C_OFF_FB1 = 1002080, C_OFF_FW2 = 1002580, C_OFF_FB2 = 1007580;
 static_assert(C_OFF_FB2 + 10 == CNN_DIM, "CNN theta layout");
 constexpr int CNN_PIX = 784, CNN_C1 = 10, CNN_C2 = 20, CNN_FLAT = 2000, CNN_FLAT_PAD = 2048, CNN_HID = 500, CNN_HID_PAD = 512;
-constexpr int CNN_G = 8;                    // images per CTA pass
-constexpr int CNN_THREADS = 256;
-constexpr int CNN_SMEM = CNN_G * CNN_PIX * 4 + CNN_G * 1440 * 4 + 25 * 12 * 4 + 16 * 4 + 90 * 20 * 8 + 32 * 4;
+constexpr int CNN_G = 8;                    // images per pass
+constexpr int CNN_THREADS = 256;            // 8 warps, two per SM sub-partition; one CTA per SM (12 warps measured slower: the 23 chunks of a step leave a longer tail)
+constexpr int CNN_P1_STRIDE = 1448;         // floats per image of the pooled conv1 activations (1440 + 8: images land on different banks)
+constexpr int CNN_IMG_BYTES = CNN_G * CNN_PIX * 4, CNN_P1_BYTES = CNN_G * CNN_P1_STRIDE * 4, CNN_STAGE_BYTES = CNN_G * 2 * CNN_FLAT_PAD * 2;
+constexpr int CNN_SMEM = 2 * CNN_IMG_BYTES + 2 * CNN_P1_BYTES + CNN_STAGE_BYTES + 25 * 12 * 4 + 16 * 4 + 90 * 2 * 12 * 4 + 32 * 4;
+static_assert(CNN_SMEM <= 226 * 1024, "shared-memory plan of cnn_conv_kernel");
+constexpr int CNN_CHUNKS1 = CNN_G * 72 / 32, CNN_CHUNKS2 = CNN_G * 20 / 32;      // warp-sized task chunks per full pass: 18 (conv1) and 5 (conv2)
 
 struct CnnConvArgs {
     const float* X;            // [n, 784] float32
@@ -35,135 +39,201 @@ struct CnnConvArgs {
     const float* theta;        // first node of the batch
     long long theta_stride;
     int nb;
-    __nv_bfloat16* out;        // fc1's A operand, tile-major [nb][mb128][64 k-tiles: 32 h, 32 l][128][64]
+    __nv_bfloat16* out;        // fc1's A operand, tile-major [nb][mb128][64 k-tiles: 32 h, 32 l][128][64]; k' = (y*10 + x)*20 + o (cnn_split_w_kernel permutes fc1.weight to match)
     int mb128;
 };
 
-// One CTA = one node of the batch (its filters stay in shared memory) x a strided range of CNN_G-image groups.
-__global__ void __launch_bounds__(CNN_THREADS, 2) cnn_conv_kernel(const CnnConvArgs g) {
-    extern __shared__ __align__(16) uint8_t cnn_smem[];
-    float* s_img = reinterpret_cast<float*>(cnn_smem);                       // [G][784]
-    float* s_p1 = s_img + CNN_G * CNN_PIX;                                  // [G][10][12][12]
-    float* s_w1 = s_p1 + CNN_G * 1440;                                      // [25 taps][12]: 10 channels + 2 zero pads
-    float* s_b1 = s_w1 + 25 * 12;                                           // [16]
-    float2* s_w2 = reinterpret_cast<float2*>(s_b1 + 16);                    // [90 taps = c*9 + ky*3 + kx][20 channels] as (w, w)
-    float* s_b2 = reinterpret_cast<float*>(s_w2 + 90 * 20);                 // [32]
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 
-    const int tid = threadIdx.x;
-    const int b = blockIdx.x % g.nb, slot = blockIdx.x / g.nb, nslots = gridDim.x / g.nb;
-    const float* th = g.theta + (long long)b * g.theta_stride;
-    for (int i = tid; i < 25 * 12; i += CNN_THREADS) { const int tap = i / 12, c = i - tap * 12; s_w1[i] = c < CNN_C1 ? __ldg(th + C_OFF_W1 + c * 25 + tap) : 0.f; }
-    if (tid < 16) s_b1[tid] = tid < CNN_C1 ? __ldg(th + C_OFF_B1 + tid) : 0.f;
-    for (int i = tid; i < 90 * 20; i += CNN_THREADS) { const int tap = i / 20, o = i - tap * 20; const float w = __ldg(th + C_OFF_W2 + o * 90 + tap); s_w2[i] = make_float2(w, w); }
-    if (tid < 32) s_b2[tid] = tid < CNN_C2 ? __ldg(th + C_OFF_B2 + tid) : 0.f;
-
-    const int ngroups = (g.n + CNN_G - 1) / CNN_G;
-    for (int grp = slot; grp < ngroups; grp += nslots) {
-        const int img0 = grp * CNN_G;
-        const int cnt = (g.n - img0) < CNN_G ? (g.n - img0) : CNN_G;
-        __syncthreads();                                                     // the previous pass is done with s_img / s_p1 (and the filters are in)
-        {
-            const float4* src = reinterpret_cast<const float4*>(g.X + (long long)img0 * CNN_PIX);
-            float4* dst = reinterpret_cast<float4*>(s_img);
-            for (int i = tid; i < cnt * (CNN_PIX / 4); i += CNN_THREADS) dst[i] = __ldg(src + i);
-        }
-        __syncthreads();
-        // ---- conv1 (5x5, 1 -> 10) + bias + ReLU + 2x2 max pool: one task = one pooled position, all 10 channels; FFMA2 over channel pairs ----
-        for (int t = tid; t < cnt * 144; t += CNN_THREADS) {
-            const int gi = t / 144, w = t - gi * 144, py = w / 12, px = w - py * 12;
-            const float* im = s_img + gi * CNN_PIX + (2 * py) * 28 + 2 * px;
-            float patch[6][6];
+// conv1 (5x5, 1 -> 10) + bias + ReLU + 2x2 max pool: one task = two horizontally adjacent pool windows (2 x 4 conv positions), all 10 channels
+__device__ __forceinline__ void cnn_conv1_task(int t, const float* s_img, float* s_p1, const float* s_w1, const float* s_b1) {
+    const int gi = t / 72, w = t - gi * 72, py = w / 6, pxp = w - py * 6;
+    const float* im = s_img + gi * CNN_PIX + (2 * py) * 28 + 4 * pxp;
+    float patch[6][8];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) {
+    for (int r = 0; r < 6; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(im + r * 28), c4 = *reinterpret_cast<const float4*>(im + r * 28 + 4);
+        patch[r][0] = a.x; patch[r][1] = a.y; patch[r][2] = a.z; patch[r][3] = a.w; patch[r][4] = c4.x; patch[r][5] = c4.y; patch[r][6] = c4.z; patch[r][7] = c4.w;
+    }
+    float2 acc[8][5];
 #pragma unroll
-                for (int q = 0; q < 3; ++q) { const float2 v = *reinterpret_cast<const float2*>(im + r * 28 + 2 * q); patch[r][2 * q] = v.x; patch[r][2 * q + 1] = v.y; }
-            }
-            float2 acc[4][5];
+    for (int p = 0; p < 8; ++p)
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+        for (int j = 0; j < 5; ++j) acc[p][j] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) acc[p][j] = make_float2(0.f, 0.f);
+    for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
-            for (int ky = 0; ky < 5; ++ky) {
+        for (int kx = 0; kx < 5; ++kx) {
+            const float* wp = s_w1 + (ky * 5 + kx) * 12;
+            const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+            const float2 wc = *reinterpret_cast<const float2*>(wp + 8);
+            const float2 wj[5] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w), wc};
 #pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
-                    const float4* wp = reinterpret_cast<const float4*>(s_w1 + (ky * 5 + kx) * 12);
-                    const float4 wa = wp[0], wb = wp[1], wc = wp[2];
-                    const float2 wj[5] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w), make_float2(wc.x, wc.y)};
+            for (int p = 0; p < 8; ++p) {
+                const float2 vv = dup2(patch[ky + (p >> 2)][kx + (p & 3)]);
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float v = patch[ky + (p >> 1)][kx + (p & 1)];
-                        const float2 vv = make_float2(v, v);
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) acc[p][j] = ffma2f(vv, wj[j], acc[p][j]);
-                    }
-                }
-            }
-            // max over the window first, then bias + ReLU: x -> relu(x + b) is monotone, so this equals pool(relu(conv + b)) bit for bit
-            float* o = s_p1 + gi * 1440 + py * 12 + px;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float m0 = fmaxf(fmaxf(acc[0][j].x, acc[1][j].x), fmaxf(acc[2][j].x, acc[3][j].x));
-                const float m1 = fmaxf(fmaxf(acc[0][j].y, acc[1][j].y), fmaxf(acc[2][j].y, acc[3][j].y));
-                o[(2 * j) * 144] = fmaxf(m0 + s_b1[2 * j], 0.f);
-                o[(2 * j + 1) * 144] = fmaxf(m1 + s_b1[2 * j + 1], 0.f);
+                for (int j = 0; j < 5; ++j) acc[p][j] = ffma2f(vv, wj[j], acc[p][j]);
             }
         }
-        __syncthreads();
-        // ---- conv2 (3x3, 10 -> 20) + bias + ReLU: one task = a 2x2 block of output positions x 10 channels; FFMA2 over horizontal position pairs ----
-        for (int t = tid; t < cnt * 50; t += CNN_THREADS) {
-            const int gi = t / 50, r = t - gi * 50, hh = r / 25, win = r - hh * 25, wy = win / 5, wx = win - wy * 5;
-            const float* p1 = s_p1 + gi * 1440 + (2 * wy) * 12 + 2 * wx;
-            float2 acc[2][10];
+    }
+    // max over the window first, then bias + ReLU: x -> relu(x + b) is monotone, so this equals pool(relu(conv + b)) bit for bit
+    float* o = s_p1 + gi * CNN_P1_STRIDE + py * 12 + 2 * pxp;
 #pragma unroll
-            for (int oy = 0; oy < 2; ++oy)
+    for (int wdw = 0; wdw < 2; ++wdw) {
 #pragma unroll
-                for (int j = 0; j < 10; ++j) acc[oy][j] = make_float2(0.f, 0.f);
-#pragma unroll 2
-            for (int c = 0; c < CNN_C1; ++c) {
-                float v[4][4];
+        for (int j = 0; j < 5; ++j) {
+            const float2 a0 = acc[2 * wdw][j], a1 = acc[2 * wdw + 1][j], a2 = acc[4 + 2 * wdw][j], a3 = acc[4 + 2 * wdw + 1][j];
+            o[(2 * j) * 144 + wdw] = fmaxf(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)) + s_b1[2 * j], 0.f);
+            o[(2 * j + 1) * 144 + wdw] = fmaxf(fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)) + s_b1[2 * j + 1], 0.f);
+        }
+    }
+}
+
+// conv2 (3x3, 10 -> 20) + bias + ReLU: one task = 2 rows x 5 columns of output positions x 10 channels; the result goes to the staging area as
+// [h | l] bf16 with k' = (y*10 + x)*20 + o (the ten channels of one position are 20 contiguous bytes)
+__device__ __forceinline__ void cnn_conv2_task(int t, const float* s_p1, __nv_bfloat16* s_out, const float* s_w2, const float* s_b2) {
+    const int gi = t / 20, r20 = t - gi * 20, hh = r20 / 10, blk = r20 - hh * 10, ry = blk >> 1, cx = blk & 1;
+    float2 acc[10][5];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const float2 a = *reinterpret_cast<const float2*>(p1 + c * 144 + rr * 12), bq = *reinterpret_cast<const float2*>(p1 + c * 144 + rr * 12 + 2);
-                    v[rr][0] = a.x; v[rr][1] = a.y; v[rr][2] = bq.x; v[rr][3] = bq.y;
-                }
+    for (int p = 0; p < 10; ++p)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
+        for (int j = 0; j < 5; ++j) acc[p][j] = make_float2(0.f, 0.f);
+    const float* p1 = s_p1 + gi * CNN_P1_STRIDE + (2 * ry) * 12 + 5 * cx;
+#pragma unroll 1
+    for (int c = 0; c < CNN_C1; ++c) {
+        float v[4][7];
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float4* wp = reinterpret_cast<const float4*>(s_w2 + (c * 9 + ky * 3 + kx) * 20 + hh * 10);
-                        float2 wd[10];
+        for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) { const float4 q = wp[j]; wd[2 * j] = make_float2(q.x, q.y); wd[2 * j + 1] = make_float2(q.z, q.w); }
+            for (int q = 0; q < 7; ++q) v[rr][q] = p1[c * 144 + rr * 12 + q];
 #pragma unroll
-                        for (int oy = 0; oy < 2; ++oy) {
-                            const float2 in = make_float2(v[oy + ky][kx], v[oy + ky][kx + 1]);
+        for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                            for (int j = 0; j < 10; ++j) acc[oy][j] = ffma2f(in, wd[j], acc[oy][j]);
-                        }
-                    }
-                }
-            }
-            // bias + ReLU, split to [h | l] bf16 and store into fc1's tile-major A operand: k = o*100 + y*10 + x (torch's view(in_size, -1))
-            const int row = img0 + gi;
-            __nv_bfloat16* oblk = g.out + ((long long)b * g.mb128 + (row >> 7)) * 64ll * 8192ll + (long long)(row & 127) * 64;
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* wp = s_w2 + ((c * 9 + ky * 3 + kx) * 2 + hh) * 12;
+                const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+                const float2 wc = *reinterpret_cast<const float2*>(wp + 8);
+                const float2 wj[5] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w), wc};
 #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const int o = hh * 10 + j;
-                const float bo = s_b2[o];
+                for (int p = 0; p < 10; ++p) {
+                    const float2 vv = dup2(v[(p / 5) + ky][(p % 5) + kx]);
 #pragma unroll
-                for (int oy = 0; oy < 2; ++oy) {
-                    const float a0 = fmaxf(acc[oy][j].x + bo, 0.f), a1 = fmaxf(acc[oy][j].y + bo, 0.f);
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
-                    const int k = o * 100 + (2 * wy + oy) * 10 + 2 * wx;           // even: the pair stays inside one 64-wide k-tile
-                    __nv_bfloat16* d = oblk + (long long)(k >> 6) * 8192 + (k & 63);
-                    *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(h0, h1);
-                    *reinterpret_cast<uint32_t*>(d + 32ll * 8192) = pack_bf16x2(l0, l1);
+                    for (int j = 0; j < 5; ++j) acc[p][j] = ffma2f(vv, wj[j], acc[p][j]);
                 }
             }
         }
     }
+    __nv_bfloat16* so = s_out + gi * (2 * CNN_FLAT_PAD);
+#pragma unroll
+    for (int p = 0; p < 10; ++p) {
+        const int pos = (2 * ry + p / 5) * 10 + 5 * cx + (p % 5);
+        uint32_t* dh = reinterpret_cast<uint32_t*>(so + pos * 20 + hh * 10);
+        uint32_t* dl = reinterpret_cast<uint32_t*>(so + CNN_FLAT_PAD + pos * 20 + hh * 10);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float a0 = fmaxf(acc[p][j].x + s_b2[hh * 10 + 2 * j], 0.f), a1 = fmaxf(acc[p][j].y + s_b2[hh * 10 + 2 * j + 1], 0.f);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+            dh[j] = pack_bf16x2(h0, h1);
+            dl[j] = pack_bf16x2(__float2bfloat16_rn(a0 - __bfloat162float(h0)), __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+        }
+    }
+}
+
+// One CTA per SM = one node of the batch (its filters stay in shared memory) x a strided range of CNN_G-image groups, software-pipelined over the groups:
+// in one compute phase the CTA's 8 warps pull warp-sized task chunks from a shared counter — first the 5 conv2 chunks of group i (reading its pooled
+// activations, writing the staging area), then the 18 conv1 chunks of group i+1 (reading its image tile, writing ITS pooled activations) — so every SM
+// sub-partition stays busy whatever the chunk sizes (a static split leaves one of the four idle for half of each phase: ncu r3d, FMA pipe 54 %);
+// then the staging area is copied out with full 128-byte rows while the image tile of group i+2 is loaded.
+//
+// Shared-memory bandwidth, not the FMA pipe, is what a direct convolution runs out of first (ncu r3c on the first version: shared wavefronts 71 %, FMA
+// pipe 51 %): a warp-wide load delivers 128 B per clock to the register file even when every lane reads the same filter tap.  Both convolutions therefore
+// pack two OUTPUT CHANNELS per fma.rn.f32x2 (the filter taps are read as natural (w_c, w_c+1) pairs), every thread owns 8 (conv1) / 10 (conv2) output
+// positions so that one 10-channel tap vector (10 registers from shared memory) feeds 40 / 50 packed FMAs.
+__global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv_kernel(const CnnConvArgs g) {
+    extern __shared__ __align__(16) uint8_t cnn_smem[];
+    float* s_img0 = reinterpret_cast<float*>(cnn_smem);                                       // 2 x [G][784]
+    float* s_p10 = reinterpret_cast<float*>(cnn_smem + 2 * CNN_IMG_BYTES);                    // 2 x [G][10][12][12] (+8 pad per image)
+    __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(cnn_smem + 2 * CNN_IMG_BYTES + 2 * CNN_P1_BYTES);   // staging [G][2 planes][2048]
+    float* s_w1 = reinterpret_cast<float*>(cnn_smem + 2 * CNN_IMG_BYTES + 2 * CNN_P1_BYTES + CNN_STAGE_BYTES);  // [25 taps][12]: 10 channels + 2 pads
+    float* s_b1 = s_w1 + 25 * 12;                                                             // [16]
+    float* s_w2 = s_b1 + 16;                                                                  // [90 taps = c*9 + ky*3 + kx][2 channel halves][12]
+    float* s_b2 = s_w2 + 90 * 2 * 12;                                                         // [32]
+    __shared__ int s_ctr;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t ctr_addr = smem_u32(&s_ctr);
+    const int b = blockIdx.x % g.nb, slot = blockIdx.x / g.nb, nslots = gridDim.x / g.nb;
+    const float* th = g.theta + (long long)b * g.theta_stride;
+    for (int i = tid; i < 25 * 12; i += CNN_THREADS) { const int tap = i / 12, c = i - tap * 12; s_w1[i] = c < CNN_C1 ? __ldg(th + C_OFF_W1 + c * 25 + tap) : 0.f; }
+    if (tid < 16) s_b1[tid] = tid < CNN_C1 ? __ldg(th + C_OFF_B1 + tid) : 0.f;
+    for (int i = tid; i < 90 * 24; i += CNN_THREADS) { const int tap = i / 24, r = i - tap * 24, hh = r / 12, j = r - hh * 12; s_w2[i] = j < 10 ? __ldg(th + C_OFF_W2 + (hh * 10 + j) * 90 + tap) : 0.f; }
+    if (tid < 32) s_b2[tid] = tid < CNN_C2 ? __ldg(th + C_OFF_B2 + tid) : 0.f;
+
+    const int ngroups = (g.n + CNN_G - 1) / CNN_G;
+    auto group_cnt = [&](int grp) { const int rem = g.n - grp * CNN_G; return rem < CNN_G ? rem : CNN_G; };
+    // asynchronous (cp.async, 16 bytes per request): the tile of pass s+1 lands while pass s computes
+    auto load_images = [&](int grp, float* dst_img) {
+        const float* src = g.X + (long long)grp * CNN_G * CNN_PIX;
+        const uint32_t dst = smem_u32(dst_img);
+        const int nv = group_cnt(grp) * (CNN_PIX / 4);
+        for (int i = tid; i < nv; i += CNN_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + 4 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // pipeline step s = 0 .. npass: conv2 of my pass s-1 and conv1 of my pass s share one compute phase
+    const int npass = slot < ngroups ? (ngroups - slot + nslots - 1) / nslots : 0;
+    if (npass > 0) load_images(slot, s_img0);
+    if (tid == 0) s_ctr = 0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int s = 0; s <= npass; ++s) {
+        const int cur = s & 1, prv = cur ^ 1;
+        if (s + 1 < npass) load_images(slot + (s + 1) * nslots, s_img0 + prv * (CNN_G * CNN_PIX));   // the image tile conv1 read in the previous step is free
+        const int grp1 = slot + s * nslots, grp2 = slot + (s - 1) * nslots;            // conv1's group (if s < npass), conv2's group (if s > 0)
+        const int n2 = s > 0 ? (group_cnt(grp2) * 20 + 31) / 32 : 0, t2 = s > 0 ? group_cnt(grp2) * 20 : 0;
+        const int n1 = s < npass ? (group_cnt(grp1) * 72 + 31) / 32 : 0, t1 = s < npass ? group_cnt(grp1) * 72 : 0;
+        const float* img = s_img0 + cur * (CNN_G * CNN_PIX);
+        float* p1w = s_p10 + cur * (CNN_G * CNN_P1_STRIDE);
+        const float* p1r = s_p10 + prv * (CNN_G * CNN_P1_STRIDE);
+        for (;;) {
+            int id = 0;
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(id) : "r"(ctr_addr) : "memory");   // (atomicAdd on the generic address cost an S2R SR_CgaCtaId per chunk: 7 % of the stall samples, ncu r3g)
+            id = __shfl_sync(0xffffffffu, id, 0);
+            if (id >= n2 + n1) break;
+            if (id < n2) { const int t = id * 32 + lane; if (t < t2) cnn_conv2_task(t, p1r, s_out, s_w2, s_b2); }
+            else { const int t = (id - n2) * 32 + lane; if (t < t1) cnn_conv1_task(t, img, p1w, s_w1, s_b1); }
+        }
+        __syncthreads();                                                     // staging complete, pooled activations of the next group complete
+        if (tid == 0) s_ctr = 0;
+        if (s > 0) {
+            // coalesced copy-out: per image and plane 250 16-byte vectors (k' < 2000; the pad columns stay zero from the allocation), 8 vectors = one 128-byte row of a k-tile
+            const int img0 = grp2 * CNN_G, nv = group_cnt(grp2) * 500;
+            for (int i = tid; i < nv; i += CNN_THREADS) {
+                const int im = i / 500, r = i - im * 500, plane = r / 250, vq = r - plane * 250;
+                const int row = img0 + im, kt = vq >> 3, kin = (vq & 7) * 8;
+                const uint4 val = *reinterpret_cast<const uint4*>(s_out + im * (2 * CNN_FLAT_PAD) + plane * CNN_FLAT_PAD + vq * 8);
+                __nv_bfloat16* d = g.out + (((long long)b * g.mb128 + (row >> 7)) * 64ll + plane * 32 + kt) * 8192ll + (long long)(row & 127) * 64 + kin;
+                *reinterpret_cast<uint4*>(d) = val;
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+}
+
+// fc1.weight [500, 2000] (torch column k = o*100 + y*10 + x) -> bf16 [nb][512][2 * 2048] = [h | l] with the columns permuted to the conv kernel's
+// k' = (y*10 + x)*20 + o, zero padded
+__global__ void cnn_split_w_kernel(const float* __restrict__ theta, long long theta_stride, __nv_bfloat16* __restrict__ out, int nb) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)CNN_HID_PAD * CNN_FLAT_PAD;
+    if (i >= per * nb) return;
+    const int b = (int)(i / per); const long long rem = i - b * per;
+    const int r = (int)(rem / CNN_FLAT_PAD), c = (int)(rem - (long long)r * CNN_FLAT_PAD);
+    float v = 0.f;
+    if (r < CNN_HID && c < CNN_FLAT) { const int o = c % 20, pos = c / 20; v = theta[b * theta_stride + C_OFF_FW1 + (long long)r * CNN_FLAT + o * 100 + pos]; }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+    __nv_bfloat16* o2 = out + ((long long)b * CNN_HID_PAD + r) * (2ll * CNN_FLAT_PAD);
+    o2[c] = h; o2[CNN_FLAT_PAD + c] = l;
 }
 
 __global__ void cnn_gather_bias_kernel(const float* __restrict__ theta, long long theta_stride, float* __restrict__ out, int nb) {
@@ -253,7 +323,7 @@ int pmp_set_data_cnn(pmp_ctx* c, const float* X, const int64_t* labels, int64_t 
     s->n_local = n_local; s->n_global = n_global;
     s->nb = getenv("PMP_CNN_BATCH") ? atoi(getenv("PMP_CNN_BATCH")) : 8;
     if (s->nb < 1) s->nb = 1;
-    if (s->nb > 2 * c->sm_count) s->nb = 2 * c->sm_count;
+    if (s->nb > c->sm_count) s->nb = c->sm_count;
     std::vector<int> lab32((size_t)n_local);
     for (int64_t i = 0; i < n_local; ++i) { PMP_REQUIRE(labels[i] >= 0 && labels[i] < NCLS, "label %lld out of range at row %lld", (long long)labels[i], (long long)i); lab32[i] = (int)labels[i]; }
     const long long mb128 = (n_local + 127) / 128;
@@ -290,10 +360,10 @@ int pmp_cnn_loglik(pmp_ctx* c) {
         const int nb = (P - p0) < s->nb ? (P - p0) : s->nb;
         const float* th = c->d_props + (long long)p0 * CNN_DIM;
         long long t = (long long)nb * CNN_HID_PAD * CNN_FLAT_PAD;
-        split2_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, CNN_DIM, C_OFF_FW1, CNN_HID, CNN_FLAT, CNN_HID_PAD, CNN_FLAT_PAD, s->w, nb);
+        cnn_split_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, CNN_DIM, s->w, nb);
         cnn_gather_bias_kernel<<<(nb * CNN_HID_PAD + 255) / 256, 256, 0, c->stream>>>(th, CNN_DIM, s->bias, nb);
         CnnConvArgs ca{s->x32, M, th, CNN_DIM, nb, s->a2, mb128};
-        int per_node = (2 * c->sm_count) / nb;
+        int per_node = c->sm_count / nb;
         const int ngroups = (M + CNN_G - 1) / CNN_G;
         if (per_node > ngroups) per_node = ngroups;
         if (per_node < 1) per_node = 1;
