@@ -228,6 +228,28 @@ int pmp_set_data_glm(pmp_ctx* ctx, const float* X, const float* y, int64_t n_loc
  * `weights[all] = exp(-loss(proposal_nets[all]))` PMP_CNN.py:119-120 for PMP_TARGET_CNN; sharded by rows like the FC target. */
 int pmp_set_data_cnn(pmp_ctx* ctx, const float* X, const int64_t* labels, int64_t n_local, int64_t n_offset, int64_t n_global);
 
+/* ---- gradient (HMC) variants: complex_nets/Cifar-10/cifar_{SP,MP,PMP}hmc.py, "Bayesian Network Training"/main.py.
+ * The potential's gradient is the caller's (autograd through an arbitrary network) and is handed over as a DEVICE pointer, like the log-targets of
+ * PMP_TARGET_EXTERNAL; the leapfrog arithmetic, the kinetic energies and the acceptance run on the device.  All float pointers below are device pointers.
+ *   begin: p0 = p_init (or p_scale * N(0,1) from the Philox stream (seed, iteration, momentum stream, stream_index*dim + i));  *ke_init = |p0|^2/2;
+ *          p = p0 + sign*step*grad_parent/2;  theta_child = theta_parent + sign*step*p          (cifar_PMPhmc.py:128-147, cifar_MPhmc.py:104-125)
+ *   end:   p += sign*step*grad_child/2;  *ke_final = |p|^2/2                                     (cifar_PMPhmc.py:148-162)
+ *   accept: weights B of the P nodes and one categorical draw with the uniform u (inverse CDF in place of torch.multinomial).
+ *          nets_loss[j] = -CrossEntropy of node j (host).  Tree rules: ke_out[c] / ke_in[c] = kinetic energy of the momentum drawn at the parent
+ *          of node c for the edge to c / of the momentum that arrived at c (index 0 unused).  MP: ke_out[j] = |p_s[j]|^2/2.  SP: P = 2, ke_out = {K_0, K_1},
+ *          index = 1 iff exp(temperature * (-(K_0 + nl_0) + (nl_1 + K_1))) > u (cifar_SPhmc.py:118-126, temperature 1000). */
+typedef enum pmp_hmc_rule {
+    PMP_HMC_RULE_SP = 0,          /* cifar_SPhmc.py:77-137 */
+    PMP_HMC_RULE_MP = 1,          /* cifar_MPhmc.py:77-86  */
+    PMP_HMC_RULE_TREE_CIFAR = 2,  /* cifar_PMPhmc.py:76-108: prod_c max(0, 1 - w_old/w_new) | min(1, w_new/w_old) */
+    PMP_HMC_RULE_TREE_BNN = 3     /* main.py:67-103: the normalised pair w_new/(w_new + w_old) per level */
+} pmp_hmc_rule;
+int pmp_hmc_leapfrog_begin(pmp_ctx* ctx, const float* theta_parent, const float* grad_parent, float* theta_child, float* p_child, const float* p_init /* nullable */,
+                           int64_t dim, float step, float sign, float p_scale, uint64_t stream_index, double* ke_init /* host */);
+int pmp_hmc_leapfrog_end(pmp_ctx* ctx, float* p_child, const float* grad_child, int64_t dim, float step, float sign, double* ke_final /* host */);
+int pmp_hmc_accept(pmp_ctx* ctx, int rule, int P, const double* nets_loss, const double* ke_out, const double* ke_in /* nullable for SP, MP */, double u,
+                   double temperature, float* weights_out /* nullable, host [P] */, int32_t* index_out /* host */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -575,6 +575,153 @@ def cnn_loss_torch32(X, y, theta, div=10.0):
         return float(torch.nn.CrossEntropyLoss()(z, torch.from_numpy(np.asarray(y, dtype=np.int64))) / div)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# HMC variants (complex_nets/Cifar-10/cifar_{SP,MP,PMP}hmc.py, "Bayesian Network Training"/main.py): acceptance weights and the fit loops
+STREAM_MOMENTUM = 4
+HMC_SP, HMC_MP, HMC_TREE_CIFAR, HMC_TREE_BNN = range(4)
+
+
+def hmc_weights(rule, nl, ke_out, ke_in=None):
+    """B as step() hands it to torch.multinomial, float32 like the reference's tensors.  Tree rules: cifar_PMPhmc.py:77-108 / main.py:67-103 with
+    ke_out[c] = |p_s[parent(c)][c]|^2/2 and ke_in[c] = |p_s[c][parent(c)]|^2/2 (indexed by the child c); MP: cifar_MPhmc.py:79-86 with ke_out[j] = |p_s[j]|^2/2."""
+    f = np.float32
+    nl = np.asarray(nl, dtype=f); ko = np.asarray(ke_out, dtype=f)
+    P = len(nl)
+    with np.errstate(all="ignore"):
+        if rule == HMC_MP:
+            A = np.zeros(P, dtype=f)
+            for j in range(1, P):
+                A[j] = np.exp(min(f(0), f(f(f(nl[j] - ko[j]) - nl[0]) + ko[0])))
+            A[0] = f(P - 1) - A.sum(dtype=f)
+        else:
+            ki = np.asarray(ke_in, dtype=f)
+            depth = int(round(math.log2(P)))
+            A = np.ones(P, dtype=f)
+            for a in range(P):
+                for c in range(depth):
+                    j = 2 ** (c + 1); half = j // 2
+                    m = a % j                                                  # the `judg` reduction loop, cifar_PMPhmc.py:84-93
+                    if m < half:
+                        w_new = np.exp(f(nl[m] - ko[m + half])); w_old = np.exp(f(nl[m + half] - ki[m + half]))
+                        if rule == HMC_TREE_CIFAR:
+                            A[a] = A[a] * max(f(0), f(f(1) - f(w_old / w_new)))
+                        else:
+                            w_old = np.minimum(f(1), f(w_old / w_new)); w_new = np.maximum(f(0), f(f(1) - f(w_old / w_new)))   # torch.min / torch.max propagate NaN; the CIFAR script's Python min / max do not
+                            A[a] = f(A[a] * w_new) / f(w_new + w_old)
+                    else:
+                        w_new = np.exp(f(nl[m] - ki[m])); w_old = np.exp(f(nl[m - half] - ko[m]))
+                        if rule == HMC_TREE_CIFAR:
+                            A[a] = A[a] * min(f(1), f(w_new / w_old))
+                        else:
+                            w_new = np.minimum(f(1), f(w_new / w_old)); w_old = np.maximum(f(0), f(f(1) - f(w_new / w_old)))
+                            A[a] = f(A[a] * w_new) / f(w_new + w_old)
+    B = A.copy()
+    B[np.isnan(B)] = 1; B[np.isinf(B)] = 1
+    return B
+
+
+def hmc_momentum(seed, it, stream_index, dim):
+    """what hmc.cu draws for torch.randn(d): float32(N(0,1)) from the momentum stream; the caller multiplies by 0.0005 like the scripts"""
+    return stream_normals(seed, it, STREAM_MOMENTUM, stream_index * dim, dim).astype(np.float32)
+
+
+def _flat_grad(net):
+    import torch
+    return torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+
+
+def hmc_fit_restated(kind, net, X, y, num_steps, seed, N=3, step_size=0.1, device="cpu"):
+    """The fit loops of the four HMC scripts restated on top of torch autograd (same module copies, the same accumulating .grad buffers, the same
+    float32 leapfrog arithmetic), with the scripts' unseeded generators replaced by this repo's streams: torch.randn(d) -> hmc_momentum, torch.multinomial /
+    torch.rand -> inverse CDF / comparison with stream_uniforms(.., STREAM_DRAW), random.uniform -> STREAM_PICK.  Returns (loss list, accepted indices, final net).
+    kind: 'SP' cifar_SPhmc.py:77-137, 'MP' cifar_MPhmc.py:91-153, 'PMP' cifar_PMPhmc.py:114-172, 'BNN' main.py:104-172."""
+    import copy
+    import torch
+    loss_fn = torch.nn.CrossEntropyLoss().to(device)
+    d = sum(p.numel() for p in net.parameters())
+    losses, picks = [], []
+
+    def randn(it, si):
+        return torch.from_numpy(hmc_momentum(seed, it, si, d)).to(device)
+
+    def kick_drift(child, parent_for_grad, p, sign):
+        du = _flat_grad(parent_for_grad).reshape(d)
+        p += sign * step_size * du / 2
+        off = 0
+        for par in child.parameters():
+            k = par.numel()
+            par.data += sign * step_size * p[off:off + k].reshape(par.data.shape)
+            off += k
+
+    for s in range(num_steps):
+        u = float(stream_uniforms(seed, s, STREAM_DRAW, 0, 1)[0])
+        if kind == "SP":
+            prop = copy.deepcopy(net)
+            p_old = randn(s, 0) * 0.0005
+            p_new = copy.deepcopy(p_old).to(device)
+            x0 = -loss_fn(net(X), y)
+            H0 = (p_old * p_old).sum() / 2 + x0
+            x0.backward()
+            kick_drift(prop, net, p_new, 1.0)
+            x1 = -loss_fn(prop(X), y)
+            x1.backward()
+            p_new += step_size * _flat_grad(prop).reshape(d) / 2
+            p1 = (p_new * p_new).sum() / 2
+            x1 = -loss_fn(prop(X), y)
+            H1 = x1 + p1
+            acc = bool(torch.exp((-H0 + H1) * 1000) > u)
+            if acc:
+                net = prop
+                losses.append(float(-x1.data))
+            else:
+                losses.append(float(-x0.data))
+            picks.append(int(acc))
+            continue
+        nets = [None] * (N + 1); nl = [None] * (N + 1)
+        nets[0] = copy.deepcopy(net).to(device)
+        if kind == "MP":
+            p_s = [None] * (N + 1)
+            p_s[0] = randn(s, 0) * 0.0005
+            ranint = int(1 + float(stream_uniforms(seed, s, STREAM_PICK, 0, 1)[0]) * N)       # int(random.uniform(1, N + 1))
+            sign = 1.0
+            for i in range(N):
+                if i >= ranint:
+                    sign = -1.0
+                j = i + 1
+                nets[j] = copy.deepcopy(nets[i]).to(device)
+                p_s[j] = copy.deepcopy(p_s[i])
+                nl[i] = -loss_fn(nets[i](X), y)
+                nl[i].backward()
+                kick_drift(nets[j], nets[i], p_s[j], sign)
+                nl[j] = -loss_fn(nets[j](X), y)
+                nl[j].backward()
+                p_s[j] += sign * step_size * _flat_grad(nets[j]).reshape(d) / 2
+            ko = [float((p * p).sum() / 2) for p in p_s]
+            B = hmc_weights(HMC_MP, [float(v.detach()) for v in nl], ko)
+        else:
+            depth = int(round(math.log2(N + 1)))
+            ko = [0.0] * (N + 1); ki = [0.0] * (N + 1)
+            for i in range(depth):
+                j = 2 ** i
+                for k in range(j):
+                    p0 = randn(s, k + j) * 0.0005
+                    nets[k + j] = copy.deepcopy(nets[k]).to(device)
+                    p = copy.deepcopy(p0)
+                    nl[k] = -loss_fn(nets[k](X), y)
+                    nl[k].backward()
+                    kick_drift(nets[k + j], nets[k], p, 1.0)
+                    nl[k + j] = -loss_fn(nets[k + j](X), y)
+                    nl[k + j].backward()
+                    p += step_size * _flat_grad(nets[k + j]).reshape(d) / 2
+                    ko[k + j] = float((p0 * p0).sum() / 2); ki[k + j] = float((p * p).sum() / 2)
+            B = hmc_weights(HMC_TREE_CIFAR if kind == "PMP" else HMC_TREE_BNN, [float(v.detach()) for v in nl], ko, ki)
+        I = int(draw_numpy(B.astype(np.float64), [u])[0])
+        net = nets[I]
+        losses.append(float(-nl[I].detach()))
+        picks.append(I)
+    return losses, picks, net
+
+
 # ---- d-dimensional GLM heads (extension of the simple-net model, SURVEY 8f rank 1; no reference counterpart: plain binary64) ----
 def loglik_glm_f64(X, y, thetas, kind, scale=1.0):
     """kind 'logistic': sum_i log sigmoid(s_i x_i.theta), s_i = 2 y_i - 1.  kind 'gauss': theta = (coefficients, sigma),

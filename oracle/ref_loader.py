@@ -116,3 +116,33 @@ def load_cnn(kind, X, y, device="cpu"):
         src += "".join(lines[a:b]) + "\n"
     exec(compile(src, path, "exec"), ns)
     return ns
+
+
+def load_hmc(kind, X, y, device="cpu"):
+    """The HMC variants: complex_nets/Cifar-10/cifar_{SP,MP,PMP}hmc.py (LeNet + the optimizer class) and
+    "Bayesian Network Training"/main.py (class bnnPMPHmc), with the dataset download replaced by injected globals X, y."""
+    import copy
+    import math
+    import random
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from torch import nn
+    rel, ranges = {"PMP": ("complex_nets/Cifar-10/cifar_PMPhmc.py", [(24, 56), (64, 172)]),
+                   "MP": ("complex_nets/Cifar-10/cifar_MPhmc.py", [(26, 58), (66, 153)]),
+                   "SP": ("complex_nets/Cifar-10/cifar_SPhmc.py", None),
+                   "BNN": ("complex_nets/Bayesian Network Training/main.py", [(54, 172)])}[kind]
+    path = os.path.join(REF, rel)
+    with open(path, encoding="utf-8-sig") as f:
+        lines = f.readlines()
+    if ranges is None:                       # SP: from `class Flatten` to the end of HMCOptimizer.fit
+        a = next(i for i, l in enumerate(lines) if l.startswith("class Flatten"))
+        b = next(i for i, l in enumerate(lines) if l.startswith("network = ") or l.startswith("network=") or l.startswith("init_network"))
+        ranges = [(a, b)]
+    ns = {"torch": torch, "F": F, "nn": nn, "copy": copy, "math": math, "np": np, "random": random, "tqdm": lambda it: it, "device": device,
+          "X": X, "y": y, "x_test": X[:8], "y_test": y[:8], "print": lambda *a, **k: None}
+    src = ""
+    for a, b in ranges:
+        src += "".join(lines[a:b]) + "\n"
+    exec(compile(src, path, "exec"), ns)
+    return ns

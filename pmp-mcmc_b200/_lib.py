@@ -16,6 +16,7 @@ TARGET_LINEAR_GAUSS, TARGET_NORMAL1D, TARGET_BANANA, TARGET_STDNORMAL, TARGET_FC
 ALGO_MH, ALGO_BARKER, ALGO_MP, ALGO_PSP, ALGO_PMP, ALGO_TABLE = range(6)
 DRAW_PYTHON, DRAW_CUDA, DRAW_SINGLE = range(3)
 FLAG_QUIRK_LEVEL_MOD, FLAG_QUIRK_TABLE_CONST, FLAG_STANDARDIZE, FLAG_KERNEL_MEAN, FLAG_NO_KERNEL_TERM, FLAG_UNIFORM_PROPOSAL = 1, 2, 4, 8, 16, 32
+HMC_RULE_SP, HMC_RULE_MP, HMC_RULE_TREE_CIFAR, HMC_RULE_TREE_BNN = range(4)
 TRACE_STATE, TRACE_NEXT, TRACE_DRAWS, TRACE_SAMPLES, TRACE_LOGW = 1, 2, 4, 8, 16
 
 EXPORTS = [
@@ -27,6 +28,7 @@ EXPORTS = [
     "pmp_chains_read_states", "pmp_chains_read_samples", "pmp_chains_run_timed", "pmp_set_data_fc", "pmp_stream_uniforms",
     "pmp_stream_normals", "pmp_time_sweep", "pmp_share_data", "pmp_run_multi", "pmp_run_multi_timed",
     "pmp_peer_exchange_handle", "pmp_peer_exchange_attach", "pmp_trace_diagnostics", "pmp_set_data_glm", "pmp_set_data_cnn",
+    "pmp_hmc_leapfrog_begin", "pmp_hmc_leapfrog_end", "pmp_hmc_accept",
 ]
 
 
@@ -106,6 +108,9 @@ def load():
     L.pmp_chains_run_timed.argtypes = [vp, i64, i32, ctypes.POINTER(ctypes.c_float)]
     L.pmp_set_data_fc.argtypes = [vp, vp, vp, i64, i64, i64]
     L.pmp_set_data_cnn.argtypes = [vp, vp, vp, i64, i64, i64]
+    L.pmp_hmc_leapfrog_begin.argtypes = [vp, vp, vp, vp, vp, vp, i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint64, vp]
+    L.pmp_hmc_leapfrog_end.argtypes = [vp, vp, vp, i64, ctypes.c_float, ctypes.c_float, vp]
+    L.pmp_hmc_accept.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp]
     L.pmp_stream_uniforms.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_stream_normals.argtypes = [u64, u64, u32, u64, i64, vp]
     L.pmp_share_data.argtypes = [vp, vp]
@@ -388,6 +393,27 @@ class Context:
         if X.ndim != 2 or len(X) != len(y):
             raise ValueError("X must be [n, d] and y [n]")
         self._chk(self.L.pmp_set_data_glm(self.h, _ptr(X), _ptr(y), len(y), n_offset, len(y) if n_global is None else n_global, X.shape[1]))
+
+    # ---- HMC variants (hmc.cu): every tensor argument is a torch CUDA float32 tensor (device pointers cross the C-ABI)
+    def hmc_leapfrog_begin(self, theta_parent, grad_parent, theta_child, p_child, step, sign=1.0, p_scale=0.0005, stream_index=0, p_init=None):
+        ke = ctypes.c_double(0.0)
+        self._chk(self.L.pmp_hmc_leapfrog_begin(self.h, theta_parent.data_ptr(), grad_parent.data_ptr(), theta_child.data_ptr(), p_child.data_ptr(),
+                                                 None if p_init is None else p_init.data_ptr(), theta_parent.numel(), step, sign, p_scale, stream_index, ctypes.byref(ke)))
+        return ke.value
+
+    def hmc_leapfrog_end(self, p_child, grad_child, step, sign=1.0):
+        ke = ctypes.c_double(0.0)
+        self._chk(self.L.pmp_hmc_leapfrog_end(self.h, p_child.data_ptr(), grad_child.data_ptr(), p_child.numel(), step, sign, ctypes.byref(ke)))
+        return ke.value
+
+    def hmc_accept(self, rule, nets_loss, ke_out, ke_in=None, u=0.5, temperature=1000.0):
+        nl = np.ascontiguousarray(nets_loss, dtype=np.float64)
+        ko = np.ascontiguousarray(ke_out, dtype=np.float64)
+        ki = None if ke_in is None else np.ascontiguousarray(ke_in, dtype=np.float64)
+        w = np.zeros(len(nl), dtype=np.float32)
+        idx = ctypes.c_int32(-1)
+        self._chk(self.L.pmp_hmc_accept(self.h, rule, len(nl), _ptr(nl), _ptr(ko), None if ki is None else _ptr(ki), float(u), float(temperature), _ptr(w), ctypes.byref(idx)))
+        return w, int(idx.value)
 
     def set_data_cnn(self, X, labels, n_offset=0, n_global=None):
         X = np.ascontiguousarray(X, dtype=np.float32).reshape(len(labels), -1)

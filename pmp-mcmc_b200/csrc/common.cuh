@@ -125,6 +125,7 @@ struct pmp_ctx {
     void* fc = nullptr;
     void* glm = nullptr;
     void* cnn = nullptr;
+    void* d_hmc = nullptr;             // HMC variants: kinetic energies, acceptance inputs / outputs (hmc.cu)
 
     // peer-memory exchange of the per-node sums (world > 1, pmp_peer_exchange_*): own buffer + the peers' buffers mapped with CUDA IPC
     unsigned long long* d_xchg = nullptr;

@@ -1,0 +1,206 @@
+// hmc.cu — gradient (HMC) variants of the multi-proposal samplers.
+//
+// Reference: complex_nets/Cifar-10/cifar_SPhmc.py:77-137 (one leapfrog proposal, Metropolis test), cifar_MPhmc.py:77-140 (a leapfrog path of N
+// nodes, weights relative to node 0), cifar_PMPhmc.py:76-171 and "Bayesian Network Training"/main.py:67-172 (binary prefetch tree whose edges
+// are leapfrog steps; per-level Barker / Metropolis products over the tree).  What is on the device here:
+//   * pmp_hmc_leapfrog_begin / _end — one leapfrog step along a tree edge on flat parameter vectors: momentum draw from the Philox stream
+//     (or injected), half kick, drift, half kick, and the two kinetic energies |p|^2/2 the acceptance needs (cifar_PMPhmc.py:128-162);
+//   * pmp_hmc_accept — the acceptance weights of all P nodes from (potential, kinetic) energies and the categorical draw, for the four rules.
+// The potential's gradient is the caller's (autograd through an arbitrary torch network: LeNet+BatchNorm, torchbnn layers) and is passed as a
+// device pointer — the same contract as PMP_TARGET_EXTERNAL for the likelihood callables (nets.py).  All vectors are device pointers.
+#include <math.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace pmp {
+
+constexpr uint32_t STREAM_MOMENTUM = 4;
+constexpr int HMC_THREADS = 256;
+constexpr int HMC_MAX_P = 1024;             // nodes of an HMC tree / path (the reference runs 2 .. 32)
+
+// p0 = scale * N(0,1) (or injected); kinetic energy of p0; p = p0 + sign * step * grad / 2; theta_child = theta_parent + sign * step * p
+__global__ void hmc_begin_kernel(const float* __restrict__ theta_parent, const float* __restrict__ grad, float* __restrict__ theta_child, float* __restrict__ p_out,
+                                 const float* __restrict__ p_init, long long dim, float step, float sign, float p_scale, uint64_t seed, uint64_t iter, uint64_t idx0,
+                                 double* __restrict__ ke) {
+    double k = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
+        const float p0 = p_init ? p_init[i] : __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + (uint64_t)i), p_scale);
+        k += (double)p0 * (double)p0;
+        // the reference's float32 operation order: p += step * du_dx / 2 ; par += step * p   (cifar_PMPhmc.py:141-147, cifar_MPhmc.py:119-125)
+        const float p = __fadd_rn(p0, __fdiv_rn(__fmul_rn(sign * step, grad[i]), 2.0f));
+        p_out[i] = p;
+        theta_child[i] = __fadd_rn(theta_parent[i], __fmul_rn(sign * step, p));
+    }
+    __shared__ double red[HMC_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < HMC_THREADS / 32; ++w) s += red[w]; atomicAdd(ke, 0.5 * s); }
+}
+
+// p += sign * step * grad / 2; kinetic energy of the final momentum
+__global__ void hmc_end_kernel(float* __restrict__ p, const float* __restrict__ grad, long long dim, float step, float sign, double* __restrict__ ke) {
+    double k = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
+        const float q = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(sign * step, grad[i]), 2.0f));
+        p[i] = q;
+        k += (double)q * (double)q;
+    }
+    __shared__ double red[HMC_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < HMC_THREADS / 32; ++w) s += red[w]; atomicAdd(ke + 1, 0.5 * s); }
+}
+
+struct HmcAcceptArgs {
+    int rule, P, depth;
+    const double* nl;        // [P]  nets_loss = -CrossEntropy (the negative potential)
+    const double* ke_out;    // [P]  |p_s[parent(c)][c]|^2 / 2 indexed by the child c (tree rules); |p_s[j]|^2 / 2 (MP path)
+    const double* ke_in;     // [P]  |p_s[c][parent(c)]|^2 / 2 indexed by the child c (tree rules)
+    double u, temperature;
+    float* weights;          // [P]  B as the reference hands it to torch.multinomial
+    int* index;
+};
+
+// torch.min / torch.max (main.py) propagate NaN; the CIFAR script's Python min(tensor(1), x) / max(tensor(0), x) return the constant when x is NaN = fminf / fmaxf
+__device__ __forceinline__ float nan_min(float a, float b) { return (isnan(a) || isnan(b)) ? NAN : fminf(a, b); }
+__device__ __forceinline__ float nan_max(float a, float b) { return (isnan(a) || isnan(b)) ? NAN : fmaxf(a, b); }
+
+// float32 like the reference's torch code (the tensors are float32 there); one CTA, P <= 1024
+__global__ void hmc_accept_kernel(const HmcAcceptArgs a) {
+    __shared__ float B[HMC_MAX_P];
+    __shared__ double cdf[HMC_MAX_P];
+    const int P = a.P;
+    for (int node = threadIdx.x; node < P; node += blockDim.x) {
+        float A;
+        if (a.rule == PMP_HMC_RULE_MP) {
+            // cifar_MPhmc.py:79-82: A_j = exp(min(0, (nl_j - K_j) - (nl_0 - K_0))), A_0 = N - sum_j A_j (filled below)
+            A = node == 0 ? 0.f : expf(fminf(0.f, (float)a.nl[node] - (float)a.ke_out[node] - (float)a.nl[0] + (float)a.ke_out[0]));
+        } else if (a.rule == PMP_HMC_RULE_SP) {
+            // cifar_SPhmc.py:122-126: accept the proposal iff exp((-H_0 + H_1) * 1000) > rand, H = nl + K as the script signs them
+            A = node == 0 ? 0.f : expf((float)(a.temperature) * (-((float)a.ke_out[0] + (float)a.nl[0]) + ((float)a.nl[1] + (float)a.ke_out[1])));
+        } else {
+            A = 1.f;
+            for (int c = 0; c < a.depth; ++c) {
+                const int half = 1 << c, m = node & (2 * half - 1);          // the script's `judg` loop reduces `all` modulo 2^(c+1) (cifar_PMPhmc.py:84-93)
+                if (m < half) {
+                    const int ch = m + half;                                 // edge (m -> ch): p_s[m][ch] is the momentum drawn at m, p_s[ch][m] the one that arrived at ch
+                    const float w_new = expf((float)a.nl[m] - (float)a.ke_out[ch]);
+                    const float w_old = expf((float)a.nl[ch] - (float)a.ke_in[ch]);
+                    if (a.rule == PMP_HMC_RULE_TREE_CIFAR) A = A * fmaxf(0.f, 1.f - w_old / w_new);                      // cifar_PMPhmc.py:94-97
+                    else { const float wo = nan_min(1.f, w_old / w_new), wn = nan_max(0.f, 1.f - wo / w_new); A = A * wn / (wn + wo); }   // main.py:84-88,95
+                } else {
+                    const int par = m - half;
+                    const float w_new = expf((float)a.nl[m] - (float)a.ke_in[m]);     // p_s[m][m - half]: the momentum that arrived at m
+                    const float w_old = expf((float)a.nl[par] - (float)a.ke_out[m]);  // p_s[m - half][m]: the momentum drawn at the parent
+                    if (a.rule == PMP_HMC_RULE_TREE_CIFAR) A = A * fminf(1.f, w_new / w_old);                            // cifar_PMPhmc.py:99-102
+                    else { const float wn = nan_min(1.f, w_new / w_old), wo = nan_max(0.f, 1.f - wn / w_old); A = A * wn / (wn + wo); }   // main.py:89-95
+                }
+            }
+        }
+        B[node] = A;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (a.rule == PMP_HMC_RULE_MP) { float s = 0.f; for (int j = 0; j < P; ++j) s += B[j]; B[0] = (float)(P - 1) - s; }
+        if (a.rule == PMP_HMC_RULE_SP) {
+            const int acc = B[1] > (float)a.u ? 1 : 0;
+            a.weights[0] = B[0]; a.weights[1] = B[1];
+            *a.index = acc;
+            return;
+        }
+        // cifar_PMPhmc.py:104-107: NaN and Inf weights become 1; then one categorical draw (inverse CDF in place of torch.multinomial)
+        double s = 0.0;
+        for (int j = 0; j < P; ++j) { float b = B[j]; if (isnan(b) || isinf(b)) b = 1.f; B[j] = b; a.weights[j] = b; s += (double)b; cdf[j] = s; }
+        int idx = P - 1;
+        for (int j = 0; j < P; ++j) if (a.u < cdf[j] / s) { idx = j; break; }          // searchsorted(cdf / cdf[-1], u, 'right')
+        *a.index = idx;
+    }
+}
+
+}  // namespace pmp
+
+using namespace pmp;
+
+extern "C" {
+
+static int hmc_scratch(pmp_ctx* c) {
+    if (!c->d_hmc) {
+        PMP_CUDA(cudaMalloc((void**)&c->d_hmc, 4096 + HMC_MAX_P * (3 * sizeof(double) + sizeof(float))));
+    }
+    return PMP_OK;
+}
+
+int pmp_hmc_leapfrog_begin(pmp_ctx* c, const float* theta_parent, const float* grad_parent, float* theta_child, float* p_child, const float* p_init, int64_t dim,
+                           float step, float sign, float p_scale, uint64_t stream_index, double* ke_init) {
+    PMP_REQUIRE(c && theta_parent && grad_parent && theta_child && p_child && dim > 0 && ke_init, "bad arguments");
+    PMP_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = hmc_scratch(c))) return rc;
+    double* ke = reinterpret_cast<double*>(c->d_hmc);
+    PMP_CUDA(cudaMemsetAsync(ke, 0, 2 * sizeof(double), c->stream));
+    long long blocks = (dim + HMC_THREADS - 1) / HMC_THREADS;
+    if (blocks > 8ll * c->sm_count) blocks = 8ll * c->sm_count;
+    hmc_begin_kernel<<<(unsigned)blocks, HMC_THREADS, 0, c->stream>>>(theta_parent, grad_parent, theta_child, p_child, p_init, dim, step, sign, p_scale,
+                                                                       c->seed, c->host_iter, stream_index * (uint64_t)dim, ke);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    PMP_CUDA(cudaMemcpyAsync(ke_init, ke, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_hmc_leapfrog_end(pmp_ctx* c, float* p_child, const float* grad_child, int64_t dim, float step, float sign, double* ke_final) {
+    PMP_REQUIRE(c && p_child && grad_child && dim > 0 && ke_final, "bad arguments");
+    PMP_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = hmc_scratch(c))) return rc;
+    double* ke = reinterpret_cast<double*>(c->d_hmc);
+    PMP_CUDA(cudaMemsetAsync(ke + 1, 0, sizeof(double), c->stream));
+    long long blocks = (dim + HMC_THREADS - 1) / HMC_THREADS;
+    if (blocks > 8ll * c->sm_count) blocks = 8ll * c->sm_count;
+    hmc_end_kernel<<<(unsigned)blocks, HMC_THREADS, 0, c->stream>>>(p_child, grad_child, dim, step, sign, ke);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    PMP_CUDA(cudaMemcpyAsync(ke_final, ke + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+int pmp_hmc_accept(pmp_ctx* c, int rule, int P, const double* nets_loss, const double* ke_out, const double* ke_in, double u, double temperature,
+                   float* weights_out, int32_t* index_out) {
+    PMP_REQUIRE(c && nets_loss && ke_out && index_out, "bad arguments");
+    PMP_REQUIRE(rule >= PMP_HMC_RULE_SP && rule <= PMP_HMC_RULE_TREE_BNN, "unknown HMC rule %d", rule);
+    PMP_REQUIRE(P >= 2 && P <= HMC_MAX_P, "P=%d out of range [2, %d]", P, HMC_MAX_P);
+    int depth = 0;
+    if (rule == PMP_HMC_RULE_SP) PMP_REQUIRE(P == 2, "the single-proposal rule takes P == 2");
+    if (rule >= PMP_HMC_RULE_TREE_CIFAR) {
+        while ((1 << depth) < P) ++depth;
+        PMP_REQUIRE((1 << depth) == P && ke_in, "the tree rules need P = 2^D nodes and both kinetic energies per edge");
+    }
+    PMP_REQUIRE(u >= 0.0 && u < 1.0, "uniform out of [0,1)");
+    PMP_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = hmc_scratch(c))) return rc;
+    uint8_t* base = reinterpret_cast<uint8_t*>(c->d_hmc) + 4096;
+    double* d_nl = reinterpret_cast<double*>(base);
+    double* d_ko = d_nl + HMC_MAX_P;
+    double* d_ki = d_ko + HMC_MAX_P;
+    float* d_w = reinterpret_cast<float*>(d_ki + HMC_MAX_P);
+    int* d_idx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(c->d_hmc) + 64);
+    PMP_CUDA(cudaMemcpyAsync(d_nl, nets_loss, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PMP_CUDA(cudaMemcpyAsync(d_ko, ke_out, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (ke_in) PMP_CUDA(cudaMemcpyAsync(d_ki, ke_in, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HmcAcceptArgs a{rule, P, depth, d_nl, d_ko, d_ki, u, temperature, d_w, d_idx};
+    hmc_accept_kernel<<<1, 256, 0, c->stream>>>(a);
+    c->launches++;
+    PMP_CUDA(cudaGetLastError());
+    if (weights_out) PMP_CUDA(cudaMemcpyAsync(weights_out, d_w, P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaMemcpyAsync(index_out, d_idx, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PMP_CUDA(cudaStreamSynchronize(c->stream));
+    return PMP_OK;
+}
+
+}  // extern "C"

@@ -423,7 +423,7 @@ int pmp_destroy(pmp_ctx* c) {
     for (int r = 0; r < PEER_MAX_WORLD; ++r) if (c->peer_xchg[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_xchg[r]);
     if (c->d_xchg) cudaFree(c->d_xchg);
     void* ptrs[] = {c->d_x, c->d_y, c->d_state, c->d_props, c->d_acc, c->d_lt, c->d_logw, c->d_draws, c->d_uniforms, c->d_cnt,
-                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_hs, c->d_bimg, c->d_kt_s1, c->d_kt_dj2, c->d_kt_dot};
+                    c->trace.state, c->trace.next, c->trace.draws, c->trace.samples, c->trace.logw, c->d_flush, c->d_z, c->d_done, c->d_dbg, c->d_psync, c->d_hs, c->d_bimg, c->d_kt_s1, c->d_kt_dj2, c->d_kt_dot, c->d_hmc};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
