@@ -131,6 +131,14 @@ def main():
     ctx.set_data_glm(Xg[lo:hi], yg[lo:hi], n_offset=lo, n_global=ng)
     ctx.write_proposals(thg)
     res["glm_lt"] = ctx.loglik()
+    # CNN sweep on sharded rows (same integer loss sums)
+    ncn = 1100
+    Xc = rng.standard_normal((ncn, 784)).astype(np.float32); yc = rng.integers(0, 10, size=ncn).astype(np.int64)
+    ctx.configure(L.TREE_BINARY, depth=2, dim=o.CNN_DIM, target=L.TARGET_CNN, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+    lo, hi = pdist.shard_bounds(ncn, world, rank, align=128)
+    ctx.set_data_cnn(Xc[lo:hi], yc[lo:hi], n_offset=lo, n_global=ncn)
+    ctx.set_state(o.cnn_init_theta(2)); ctx.seed(21, 0); ctx.propose()
+    res["cnn_lt"] = ctx.loglik()
     if rank == 0:
         np.savez(a.out, world=world, **res)
     ctx.close()

@@ -99,5 +99,10 @@ def test_sharded_chain_equals_single_gpu_chain(tmp_path, world):
         c.configure(L.TREE_FLAT, b=50, dim=dg, target=L.TARGET_GLM_LOGISTIC, algo=L.ALGO_TABLE, draw=L.DRAW_SINGLE, flags=L.FLAG_NO_KERNEL_TERM, alpha=0.0, scale=100.0)
         c.set_data_glm(Xg, yg); c.write_proposals(thg)
         assert np.array_equal(c.loglik(), g["glm_lt"])
+        ncn = 1100
+        Xc = rng.standard_normal((ncn, 784)).astype(np.float32); yc = rng.integers(0, 10, size=ncn).astype(np.int64)
+        c.configure(L.TREE_BINARY, depth=2, dim=o.CNN_DIM, target=L.TARGET_CNN, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+        c.set_data_cnn(Xc, yc); c.set_state(o.cnn_init_theta(2)); c.seed(21, 0); c.propose()
+        assert np.array_equal(c.loglik(), g["cnn_lt"])
     finally:
         c.close()
