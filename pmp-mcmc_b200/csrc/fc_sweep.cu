@@ -821,13 +821,18 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int et = (warp - 2) * 32 + lane;
         constexpr int CH = BN / 2;
         const uint32_t lempty0 = mapa_u32(smem_u32(&tempty_bar[0]), lead), lempty1 = mapa_u32(smem_u32(&tempty_bar[1]), lead);
-        if (EPI == EPI3_L4_NLL) {                                // once per launch: every node's 128 -> 10 layer into shared memory
-            for (int b = 0; b < g.nb; ++b) {
-                const float* th = g.theta + (long long)b * g.theta_stride;
-                for (int i = et; i < NCLS * H3; i += 32 * GEMM2_EPI_WARPS) { const int c = i / H3, jj = i - c * H3; s_w4_all[b * (H3 * 12) + jj * 12 + c] = __ldg(th + OFF_W4 + i); }
-                if (et < H3) { s_w4_all[b * (H3 * 12) + et * 12 + 10] = 0.f; s_w4_all[b * (H3 * 12) + et * 12 + 11] = 0.f; s_b3_all[b * H3 + et] = __ldg(g.dbias + (long long)b * g.dbias_stride + et); }
-                if (et < NCLS_PAD) s_b4_all[b * NCLS_PAD + et] = et < NCLS ? __ldg(th + OFF_B4 + et) : 0.f;
-            }
+        // once per launch: every node's 128 -> 10 layer into shared memory — when the batch has more nodes than slots (sharded runs batch more nodes per
+        // launch to keep the tile count up), the tile's node is loaded into slot 0 per tile instead (under the tile's MMAs)
+        auto load_l4 = [&](int b, int slot) {
+            const float* th = g.theta + (long long)b * g.theta_stride;
+            float* w4 = s_w4_all + slot * (H3 * 12);
+            for (int i = et; i < NCLS * H3; i += 32 * GEMM2_EPI_WARPS) { const int c = i / H3, jj = i - c * H3; w4[jj * 12 + c] = __ldg(th + OFF_W4 + i); }
+            if (et < H3) { w4[et * 12 + 10] = 0.f; w4[et * 12 + 11] = 0.f; s_b3_all[slot * H3 + et] = __ldg(g.dbias + (long long)b * g.dbias_stride + et); }
+            if (et < NCLS_PAD) s_b4_all[slot * NCLS_PAD + et] = et < NCLS ? __ldg(th + OFF_B4 + et) : 0.f;
+        };
+        const bool l4_per_tile = EPI == EPI3_L4_NLL && g.nb > L4_NB;
+        if (EPI == EPI3_L4_NLL && !l4_per_tile) {
+            for (int b = 0; b < g.nb; ++b) load_l4(b, b);
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         int j = 0;
@@ -837,9 +842,15 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int lrow = quarter * 32 + lane;
             const int row = m_blk * 2 * BM + (int)rank * BM + lrow;
             const bool valid = row < g.M;
-            const float* s_w4 = s_w4_all + batch * (H3 * 12);
-            const float* s_b3 = s_b3_all + batch * H3;
-            const float* s_b4 = s_b4_all + batch * NCLS_PAD;
+            if (l4_per_tile) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // everybody is done with the previous tile's copy
+                load_l4(batch, 0);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const int l4slot = l4_per_tile ? 0 : batch;
+            const float* s_w4 = s_w4_all + l4slot * (H3 * 12);
+            const float* s_b3 = s_b3_all + l4slot * H3;
+            const float* s_b4 = s_b4_all + l4slot * NCLS_PAD;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chalf * CH);
             // node 0's pre-activations do not depend on this tile's MMAs: the first chunk's loads are issued BEFORE the wait for the
             // accumulator, the next chunk's before the current one is processed (the epilogue was bound by their L2 latency: ncu r2e)
@@ -1162,7 +1173,6 @@ template <int BN, int EPI, int NSTAGE, int MC>
 static int launch_gemm3(pmp_ctx* c, const CUtensorMap& a, const CUtensorMap& a0, const CUtensorMap& b, const Gemm3Args& g) {
     constexpr size_t smem = (size_t)NSTAGE * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + (EPI == EPI3_L4_NLL ? (size_t)L4_NB * (H3 * 12 + H3 + NCLS_PAD) * sizeof(float) : 0);
     static_assert(smem <= 227 * 1024 - 8 * 1024, "shared-memory plan of fc_gemm3_kernel");
-    if (EPI == EPI3_L4_NLL && g.nb > L4_NB) { set_error("FC delta sweep: at most %d nodes per batch (PMP_FC_BATCH)", L4_NB); return PMP_ERR_UNSUPPORTED; }
     static bool attr = false;
     if (!attr) {
         PMP_CUDA(cudaFuncSetAttribute(fc_gemm3_kernel<BN, EPI, NSTAGE, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1284,7 +1294,9 @@ int pmp_set_data_fc(pmp_ctx* c, const float* X, const int64_t* labels, int64_t n
     FcState* s = new FcState();
     c->fc = s;
     s->n_local = n_local; s->n_global = n_global;
-    s->nb = getenv("PMP_FC_BATCH") ? atoi(getenv("PMP_FC_BATCH")) : 8;
+    // nodes per GEMM launch: 8 on one GPU; a shard of the rows has proportionally fewer row tiles per node, so sharded runs batch more nodes per launch
+    // (the same number of tiles, fewer launches per sweep: bench fc block at 8 GPUs, 8 nodes per launch: 201 us per batch against 126 ideal)
+    { int w = c->world < 1 ? 1 : c->world; s->nb = getenv("PMP_FC_BATCH") ? atoi(getenv("PMP_FC_BATCH")) : (8 * w > 32 ? 32 : 8 * w); }
     if (s->nb < 1) s->nb = 1;
     s->version = (getenv("PMP_FC_V1") && atoi(getenv("PMP_FC_V1"))) ? 1 : 2;
     const int planes = s->version == 2 ? 2 : 3;            // [h | l] or [h | h | l]
@@ -1386,9 +1398,9 @@ int pmp_fc_loglik(pmp_ctx* c) {
     // Contraction mode.  delta (v3, see fc_gemm3_kernel): needs proposals that are small increments about node 0 — generated by
     // pmp_propose with alpha sqrt(depth) <= 1e-3 (the reference runs alpha = 1e-4, PMP_FC.py:15); anything else (caller-supplied nodes,
     // large steps) takes the 3-product split (v2).  PMP_FC_MODE=x3 | delta overrides.
-    bool delta = s->version == 2 && s->nb <= L4_NB && !c->props_external && P > 1 &&
+    bool delta = s->version == 2 && !c->props_external && P > 1 &&
                  (double)c->cfg.alpha * sqrt((double)(c->cfg.tree == PMP_TREE_FLAT ? 1 : c->cfg.depth)) <= 1e-3;
-    if (const char* m = getenv("PMP_FC_MODE")) { if (!strcmp(m, "x3")) delta = false; else if (!strcmp(m, "delta") && s->version == 2 && s->nb <= L4_NB) delta = true; }
+    if (const char* m = getenv("PMP_FC_MODE")) { if (!strcmp(m, "x3")) delta = false; else if (!strcmp(m, "delta") && s->version == 2) delta = true; }
     if (delta) {
         // TMA multicast over clusters of two CTA pairs (layers 1, 2): built, parity-green, and SLOWER — opt-in with PMP_FC_MCAST=1.  ncu (r2q): the bytes an
         // SM ingests through the crossbar are unchanged (l1tex__m_xbar2l1tex_read_bytes 3.74 GB vs 3.71 GB per 8 nodes: multicast saves L2 reads, not SM

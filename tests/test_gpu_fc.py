@@ -209,3 +209,23 @@ def test_fc_delta_and_split_contractions_agree_on_a_deep_tree(ctx, monkeypatch):
         assert np.max(np.abs(d_dev - d_true)) <= 0.05 * np.max(np.abs(d_true)), (mode, d_dev, d_true)
     dd, dx = out["delta"] - out["delta"][0], out["x3"] - out["x3"][0]
     assert np.max(np.abs(dd - dx)) <= 0.05 * np.max(np.abs(dx))
+
+
+def test_fc_node_batch_size_does_not_change_a_bit(ctx, monkeypatch):
+    """nodes per GEMM launch (8 on one GPU, up to 32 on a shard: the fused last layer is then loaded per tile instead of once per launch) is a scheduling
+    choice: the integer loss sums of every node are the same bits"""
+    import os
+    from conftest import ROOT
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    theta0 = np.load(os.path.join(ROOT, "tests", "golden", "fc_theta0.npy"))
+    X, y = _data(1300, seed=8)
+    out = {}
+    for nb in ("8", "20", "3"):
+        monkeypatch.setenv("PMP_FC_BATCH", nb)
+        ctx.configure(L.TREE_BINARY, depth=5, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+        ctx.set_data_fc(X, y); ctx.set_state(theta0); ctx.seed(9, 0); ctx.propose()
+        out[nb] = ctx.loglik()
+    assert np.array_equal(out["8"], out["20"]) and np.array_equal(out["8"], out["3"])
+    truth = np.array([-o.fc_mean_ce_f64(X, y, ctx.read_proposals()[p]) / 10.0 for p in (0, 7, 31)])
+    np.testing.assert_allclose(out["20"][[0, 7, 31]], truth, rtol=2e-5)
