@@ -104,6 +104,18 @@ __device__ __forceinline__ float2 ffma2f(float2 a, float2 b, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2*>(&rd);
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): an epilogue thread owns 64 contiguous bytes of ITS row per 32-column chunk, so a warp access touches 32 different
+// rows — with 128-bit accesses every 32-byte sector is requested (loads) or partially written (stores) twice.  Measured on the delta kernels (ncu, 8 nodes): the stores cost 120 us
+// and node 0's pre-activation loads 77 us of a 465 us layer-1 launch whose main loop alone takes 294 us.
+struct __align__(32) u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ u32x8 ldg256(const void* p) {
+    u32x8 r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) { return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16); }
 
 struct GemmArgs {
@@ -503,13 +515,10 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (row < g.M) {
                         const int col = col0 + cc * 32, kt = col >> 6, cin = col & 63;
                         if (g.out) {
-                            uint4* d0 = reinterpret_cast<uint4*>(oblk + (long long)kt * (128 * 64) + cin);
-                            uint4* d1 = reinterpret_cast<uint4*>(oblk + (long long)(kt_half + kt) * (128 * 64) + cin);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                d0[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-                                d1[q] = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
-                            }
+                            __nv_bfloat16* d0 = oblk + (long long)kt * (128 * 64) + cin;
+                            __nv_bfloat16* d1 = oblk + (long long)(kt_half + kt) * (128 * 64) + cin;
+                            stg256(d0, hp); stg256(d0 + 16, hp + 8);
+                            stg256(d1, lp); stg256(d1 + 16, lp + 8);
                         }
                         if (g.t_out16) {
                             uint4* dt = reinterpret_cast<uint4*>(g.t_out16 + (long long)row * g.n_total + col);
@@ -861,16 +870,16 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const long long blk = (long long)batch * g.mb128 + (m_blk * 2 + (int)rank);
                 __nv_bfloat16* oblk = g.out + blk * (long long)kts * (128 * 64) + (long long)lrow * 64;
                 const __half* trow = g.t0h + (long long)(valid ? row : 0) * g.n_total + col0;
-                uint4 tq[4], tn[4];
+                u32x8 tq[2], tn[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tq[q] = __ldg(reinterpret_cast<const uint4*>(trow) + q);
+                for (int q = 0; q < 2; ++q) tq[q] = ldg256(trow + 16 * q);
                 mbar_wait(&tfull_bar[acc], use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int cc = 0; cc < CH / 32; ++cc) {
                     if (cc + 1 < CH / 32) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) tn[q] = __ldg(reinterpret_cast<const uint4*>(trow + (cc + 1) * 32) + q);
+                        for (int q = 0; q < 2; ++q) tn[q] = ldg256(trow + (cc + 1) * 32 + 16 * q);
                     }
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
@@ -888,12 +897,11 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (valid) {
                         const int col = col0 + cc * 32, kt = col >> 6, cin = col & 63;
-                        uint4* d = reinterpret_cast<uint4*>(oblk + (long long)kt * (128 * 64) + cin);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) d[q] = make_uint4(dp[4 * q], dp[4 * q + 1], dp[4 * q + 2], dp[4 * q + 3]);
+                        __nv_bfloat16* d = oblk + (long long)kt * (128 * 64) + cin;
+                        stg256(d, dp); stg256(d + 16, dp + 8);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) tq[q] = tn[q];
+                    for (int q = 0; q < 2; ++q) tq[q] = tn[q];
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -903,16 +911,16 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < NCLS / 2; ++c) z2[c] = chalf == 0 ? make_float2(s_b4[2 * c], s_b4[2 * c + 1]) : make_float2(0.f, 0.f);
                 const float* trow = g.t0f + (long long)(valid ? row : 0) * H3 + chalf * CH;
-                float4 tq[8], tn[8];
+                u32x8 tq[4], tn[4];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) tq[q] = __ldg(reinterpret_cast<const float4*>(trow) + q);
+                for (int q = 0; q < 4; ++q) tq[q] = ldg256(trow + 8 * q);
                 mbar_wait(&tfull_bar[acc], use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int cc = 0; cc < CH / 32; ++cc) {
                     if (cc + 1 < CH / 32) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) tn[q] = __ldg(reinterpret_cast<const float4*>(trow + (cc + 1) * 32) + q);
+                        for (int q = 0; q < 4; ++q) tn[q] = ldg256(trow + (cc + 1) * 32 + 8 * q);
                     }
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
@@ -930,7 +938,7 @@ fc_gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         z2[4] = ffma2f(aa, w2, z2[4]);
                     }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) tq[q] = tn[q];
+                    for (int q = 0; q < 4; ++q) tq[q] = tn[q];
                 }
                 float z[NCLS];
 #pragma unroll
