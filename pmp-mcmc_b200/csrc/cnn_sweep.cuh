@@ -26,8 +26,12 @@ constexpr long long C_OFF_W1 = 0, C_OFF_B1 = 250, C_OFF_W2 = 260, C_OFF_B2 = 206
 static_assert(C_OFF_FB2 + 10 == CNN_DIM, "CNN theta layout");
 constexpr int CNN_PIX = 784, CNN_C1 = 10, CNN_C2 = 20, CNN_FLAT = 2000, CNN_FLAT_PAD = 2048, CNN_HID = 500, CNN_HID_PAD = 512;
 constexpr int CNN_G = 8;                    // images per pass
-constexpr int CNN_THREADS = 256;            // 8 warps, two per SM sub-partition; one CTA per SM (12 warps measured slower: the 23 chunks of a step leave a longer tail)
-constexpr int CNN_P1_STRIDE = 1448;         // floats per image of the pooled conv1 activations (1440 + 8: images land on different banks)
+#ifndef CNN_THREADS_DEF
+#define CNN_THREADS_DEF 256
+#endif
+constexpr int CNN_THREADS = CNN_THREADS_DEF;            // 8 warps, two per SM sub-partition; one CTA per SM (12 warps measured slower: the 23 chunks of a step leave a longer tail)
+constexpr int CNN_P1_ROW = 13, CNN_P1_CH = 12 * CNN_P1_ROW, CNN_P1_STRIDE = 10 * CNN_P1_CH + 10;   // pooled conv1 activations [image][channel][12 rows][13]: rows of 13 floats and an image stride = 2 (mod 32)
+                                            // put the ten 2x5 position blocks of an image, and those of the next image in the same warp, on distinct banks (conv2's input loads were 2-way conflicted: ncu r3g)
 constexpr int CNN_IMG_BYTES = CNN_G * CNN_PIX * 4, CNN_P1_BYTES = CNN_G * CNN_P1_STRIDE * 4, CNN_STAGE_BYTES = CNN_G * 2 * CNN_FLAT_PAD * 2;
 constexpr int CNN_SMEM = 2 * CNN_IMG_BYTES + 2 * CNN_P1_BYTES + CNN_STAGE_BYTES + 25 * 12 * 4 + 16 * 4 + 90 * 2 * 12 * 4 + 32 * 4;
 static_assert(CNN_SMEM <= 226 * 1024, "shared-memory plan of cnn_conv_kernel");
@@ -77,14 +81,14 @@ __device__ __forceinline__ void cnn_conv1_task(int t, const float* s_img, float*
         }
     }
     // max over the window first, then bias + ReLU: x -> relu(x + b) is monotone, so this equals pool(relu(conv + b)) bit for bit
-    float* o = s_p1 + gi * CNN_P1_STRIDE + py * 12 + 2 * pxp;
+    float* o = s_p1 + gi * CNN_P1_STRIDE + py * CNN_P1_ROW + 2 * pxp;
 #pragma unroll
     for (int wdw = 0; wdw < 2; ++wdw) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const float2 a0 = acc[2 * wdw][j], a1 = acc[2 * wdw + 1][j], a2 = acc[4 + 2 * wdw][j], a3 = acc[4 + 2 * wdw + 1][j];
-            o[(2 * j) * 144 + wdw] = fmaxf(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)) + s_b1[2 * j], 0.f);
-            o[(2 * j + 1) * 144 + wdw] = fmaxf(fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)) + s_b1[2 * j + 1], 0.f);
+            o[(2 * j) * CNN_P1_CH + wdw] = fmaxf(fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)) + s_b1[2 * j], 0.f);
+            o[(2 * j + 1) * CNN_P1_CH + wdw] = fmaxf(fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y)) + s_b1[2 * j + 1], 0.f);
         }
     }
 }
@@ -98,14 +102,14 @@ __device__ __forceinline__ void cnn_conv2_task(int t, const float* s_p1, __nv_bf
     for (int p = 0; p < 10; ++p)
 #pragma unroll
         for (int j = 0; j < 5; ++j) acc[p][j] = make_float2(0.f, 0.f);
-    const float* p1 = s_p1 + gi * CNN_P1_STRIDE + (2 * ry) * 12 + 5 * cx;
+    const float* p1 = s_p1 + gi * CNN_P1_STRIDE + (2 * ry) * CNN_P1_ROW + 5 * cx;
 #pragma unroll 1
     for (int c = 0; c < CNN_C1; ++c) {
         float v[4][7];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-            for (int q = 0; q < 7; ++q) v[rr][q] = p1[c * 144 + rr * 12 + q];
+            for (int q = 0; q < 7; ++q) v[rr][q] = p1[c * CNN_P1_CH + rr * CNN_P1_ROW + q];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -152,7 +156,7 @@ __device__ __forceinline__ void cnn_conv2_task(int t, const float* s_p1, __nv_bf
 __global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv_kernel(const CnnConvArgs g) {
     extern __shared__ __align__(16) uint8_t cnn_smem[];
     float* s_img0 = reinterpret_cast<float*>(cnn_smem);                                       // 2 x [G][784]
-    float* s_p10 = reinterpret_cast<float*>(cnn_smem + 2 * CNN_IMG_BYTES);                    // 2 x [G][10][12][12] (+8 pad per image)
+    float* s_p10 = reinterpret_cast<float*>(cnn_smem + 2 * CNN_IMG_BYTES);                    // 2 x [G][10][12][13] (+10 pad per image)
     __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(cnn_smem + 2 * CNN_IMG_BYTES + 2 * CNN_P1_BYTES);   // staging [G][2 planes][2048]
     float* s_w1 = reinterpret_cast<float*>(cnn_smem + 2 * CNN_IMG_BYTES + 2 * CNN_P1_BYTES + CNN_STAGE_BYTES);  // [25 taps][12]: 10 channels + 2 pads
     float* s_b1 = s_w1 + 25 * 12;                                                             // [16]
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv_kernel(const CnnConvA
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t ctr_addr = smem_u32(&s_ctr);
-    const int b = blockIdx.x % g.nb, slot = blockIdx.x / g.nb, nslots = gridDim.x / g.nb;
+    const int b = blockIdx.x % g.nb, slot = blockIdx.x / g.nb, nslots = ((int)gridDim.x - b + g.nb - 1) / g.nb;   // CTAs b, b + nb, ... serve node b (every SM is used even when nb does not divide the SM count)
     const float* th = g.theta + (long long)b * g.theta_stride;
     for (int i = tid; i < 25 * 12; i += CNN_THREADS) { const int tap = i / 12, c = i - tap * 12; s_w1[i] = c < CNN_C1 ? __ldg(th + C_OFF_W1 + c * 25 + tap) : 0.f; }
     if (tid < 16) s_b1[tid] = tid < CNN_C1 ? __ldg(th + C_OFF_B1 + tid) : 0.f;
@@ -363,11 +367,11 @@ int pmp_cnn_loglik(pmp_ctx* c) {
         cnn_split_w_kernel<<<(unsigned)((t + 255) / 256), 256, 0, c->stream>>>(th, CNN_DIM, s->w, nb);
         cnn_gather_bias_kernel<<<(nb * CNN_HID_PAD + 255) / 256, 256, 0, c->stream>>>(th, CNN_DIM, s->bias, nb);
         CnnConvArgs ca{s->x32, M, th, CNN_DIM, nb, s->a2, mb128};
-        int per_node = c->sm_count / nb;
         const int ngroups = (M + CNN_G - 1) / CNN_G;
-        if (per_node > ngroups) per_node = ngroups;
-        if (per_node < 1) per_node = 1;
-        cnn_conv_kernel<<<dim3((unsigned)(per_node * nb)), CNN_THREADS, CNN_SMEM, c->stream>>>(ca);
+        long long ctas = c->sm_count;                                      // one CTA per SM; CTA i serves node i % nb
+        if (ctas > (long long)ngroups * nb) ctas = (long long)ngroups * nb;
+        if (ctas < nb) ctas = nb;
+        cnn_conv_kernel<<<dim3((unsigned)ctas), CNN_THREADS, CNN_SMEM, c->stream>>>(ca);
         c->launches += 3;
         PMP_CUDA(cudaGetLastError());
         Gemm2Args g{};
