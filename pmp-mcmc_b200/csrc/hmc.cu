@@ -20,8 +20,8 @@ constexpr int HMC_THREADS = 256;
 constexpr int HMC_MAX_P = 1024;             // nodes of an HMC tree / path (the reference runs 2 .. 32)
 
 // p0 = scale * N(0,1) (or injected); kinetic energy of p0; p = p0 + sign * step * grad / 2; theta_child = theta_parent + sign * step * p
-__global__ void hmc_begin_kernel(const float* __restrict__ theta_parent, const float* __restrict__ grad, float* __restrict__ theta_child, float* __restrict__ p_out,
-                                 const float* __restrict__ p_init, long long dim, float step, float sign, float p_scale, uint64_t seed, uint64_t iter, uint64_t idx0,
+__global__ void hmc_begin_kernel(const float* __restrict__ theta_parent, const float* __restrict__ grad, float* __restrict__ theta_child, float* p_out,
+                                 const float* p_init /* may alias p_out: the MP path carries one momentum buffer from node to node */, long long dim, float step, float sign, float p_scale, uint64_t seed, uint64_t iter, uint64_t idx0,
                                  double* __restrict__ ke) {
     double k = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
