@@ -661,6 +661,13 @@ fc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // float32 128 -> 10 layer + log-softmax + NLL in the epilogue exactly as in fc_gemm2_kernel (t^3_0 kept in float32).
 // Same skeleton as fc_gemm2_kernel: CTA pairs (cta_group::2), persistent, node-fastest tile order, two TMEM accumulator stages.
 enum { EPI3_DELTA_RELU = 0, EPI3_L4_NLL = 1 };
+// pipeline stages of the delta kernels, measured per layer (ncu, 8 nodes): layer 1 370 / 344 / 354 / 366 us with 3 / 4 / 5 / 6 stages, layer 2 221 / 214 / 217 us with 4 / 5 / 6
+#ifndef FC_NS1
+#define FC_NS1 4
+#endif
+#ifndef FC_NS2
+#define FC_NS2 5
+#endif
 constexpr int L4_NB = 8;                                          // nodes per launch whose last layer fits the L4_NLL kernel's shared memory
 
 struct Gemm3Args {
@@ -1444,11 +1451,11 @@ int pmp_fc_loglik(pmp_ctx* c) {
             Gemm3Args g1{}; g1.M = M; g1.nb = nb; g1.n_total = H1; g1.mb128 = mb128; g1.nk_a = D_IN_PAD / BK; g1.nk_total = D_IN_PAD / BK; g1.a_rowmajor = 1;
             g1.dbias = s->dbias; g1.dbias_stride = bias_stride; g1.t0h = s->t1; g1.out = s->da1;
             if (mcast) { if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 1>(c, s->tmX, s->tmX64, s->tmdW1, g1))) return rc; }
-            else if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 0>(c, s->tmX, s->tmX, s->tmdW1, g1))) return rc;
+            else if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, FC_NS1, 0>(c, s->tmX, s->tmX, s->tmdW1, g1))) return rc;
             Gemm3Args g2{}; g2.M = M; g2.nb = nb; g2.n_total = H2; g2.mb128 = mb128; g2.nk_a = H1 / BK; g2.nk_total = 2 * H1 / BK; g2.a_rowmajor = 0;
             g2.dbias = s->dbias + H1; g2.dbias_stride = bias_stride; g2.t0h = s->t2; g2.out = s->da2;
             if (mcast) { if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 2>(c, s->tmdA1, s->tmA2b, s->tmW2c64, g2))) return rc; }
-            else if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, 6, 0>(c, s->tmdA1, s->tmA2b, s->tmW2c, g2))) return rc;
+            else if ((rc = launch_gemm3<256, EPI3_DELTA_RELU, FC_NS2, 0>(c, s->tmdA1, s->tmA2b, s->tmW2c, g2))) return rc;
             Gemm3Args g3{}; g3.M = M; g3.nb = nb; g3.n_total = H3; g3.mb128 = mb128; g3.nk_a = H2 / BK; g3.nk_total = 2 * H2 / BK; g3.a_rowmajor = 0;
             g3.dbias = s->dbias + H1 + H2; g3.dbias_stride = bias_stride; g3.t0f = s->t3; g3.theta = th; g3.theta_stride = THETA_DIM; g3.labels = s->labels; g3.loss = s->loss + p0;
             if ((rc = launch_gemm3<128, EPI3_L4_NLL, 6, 0>(c, s->tmdA2, s->tmA3b, s->tmW3c, g3))) return rc;
