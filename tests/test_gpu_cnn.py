@@ -158,3 +158,26 @@ def test_cnn_device_resident_run_equals_stepwise(ctx):
     tr = ctx.read_trace()
     assert list(tr["next"]) == nxts and np.array_equal(ctx.get_state(), ref) and ctx.iteration() == 4
     ctx.trace_config(0, 0)
+
+
+def test_cnn_mh_sampler_against_reference_loss(ctx):
+    """MH_CNN.py:74-78,100-116: the un-divided loss of the current state and of one proposal, and the accept rule u < exp(10000 (loss - loss'))"""
+    from conftest import ROOT
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cnn_step.npz"))
+    theta0 = np.load(os.path.join(ROOT, "tests", "golden", "cnn_theta0.npy"))
+    n = int(G["s_n"])
+    X = np.random.default_rng(int(G["s_data_seed"])).standard_normal((n, 784)).astype(np.float32)
+    y = G["s_labels"].astype(np.int64)
+    props = o.propose(o.TREE_BINARY, 2, 3, o.CNN_DIM, float(G["alpha"]), theta0, int(G["prop_seed"]), 0)[:2]
+    ctx.configure(L.TREE_FLAT, b=2, dim=o.CNN_DIM, target=L.TARGET_CNN, algo=L.ALGO_MH, draw=L.DRAW_SINGLE, alpha=float(G["alpha"]), scale=1.0, mh_temperature=10000.0)
+    ctx.set_data_cnn(X, y); ctx.set_state(props[0]); ctx.seed(1, 0)
+    ctx.write_proposals(props)
+    lt = ctx.loglik()
+    np.testing.assert_allclose(-lt, G["s_MH_loss"], rtol=2e-5)
+    ratio = np.exp(10000.0 * (G["s_MH_loss"][0] - G["s_MH_loss"][1]))
+    for u in (0.5 * min(ratio, 1.0), min(0.999999, 1.5 * ratio + 1e-3)):
+        ctx.set_state(props[0]); ctx.write_proposals(props); ctx.loglik(read=False)
+        idx, nxt = ctx.accept(np.array([u]))
+        assert nxt == int(u < ratio), (u, ratio, nxt)
