@@ -214,3 +214,18 @@ def test_against_reference_mh_and_conv_mp_kernels(ctx):
     out = np.zeros(8, dtype=np.float32)
     assert ref.ref_loglik_ex(props.ctypes.data_as(fp), 8, 1, 1, 0, out.ctypes.data_as(fp), 1, ctypes.byref(ms)) == 0
     np.testing.assert_allclose(A, out.astype(np.float64), rtol=5e-5)
+
+
+@pytest.mark.parametrize("dim,tree,b,depth", [(40000, 1, 2, 5), (40001, 1, 2, 5), (50001, 2, 3, 3), (40000, 1, 2, 6)])
+def test_long_vector_tree_proposals_bit_exact(ctx, dim, tree, b, depth):
+    """level-wise proposal kernel for long parameter vectors (FC / CNN sized): one shared Philox block per element pair, tail quantiles compacted per warp —
+    the same bits as the oracle's per-element restatement, for even and odd dimensions (odd: the pairs straddle the node boundary)"""
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    rng = np.random.default_rng(dim)
+    state = rng.standard_normal(dim).astype(np.float32)
+    ctx.configure(tree, b=b, depth=depth, dim=dim, target=L.TARGET_EXTERNAL, algo=L.ALGO_TABLE, draw=L.DRAW_SINGLE, flags=L.FLAG_NO_KERNEL_TERM, alpha=3e-3, scale=1.0)
+    ctx.set_state(state); ctx.seed(77, 5); ctx.propose()
+    dev = ctx.read_proposals()
+    ref = o.propose(tree, b, depth, dim, 3e-3, state, 77, 5)
+    assert dev.shape == ref.shape and np.array_equal(dev.view(np.uint32), ref.view(np.uint32))
