@@ -327,7 +327,9 @@ def extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps):
         ms.append(max_over_ranks(ctx.run_timed(1)[0]))
     nxt = ctx.read_trace()["next"]
     ctx.propose(); ctx.sync()
-    t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = max_over_ranks(time.perf_counter() - t0)
+    sweep_s = 1e30
+    for _ in range(2):                                           # best of two: a single sweep right after the timed iterations is at the mercy of the power state
+        t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = min(sweep_s, max_over_ranks(time.perf_counter() - t0))
     lt = ctx.loglik()
     P = 1 << FC_DEPTH
     it_s = float(np.mean(ms)) * 1e-3
@@ -362,7 +364,9 @@ def extra_cnn(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps, fp32_pea
     ms = [max_over_ranks(ctx.run_timed(1)[0]) for _ in range(steps)]
     nxt = ctx.read_trace()["next"]
     ctx.propose(); ctx.sync()
-    t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = max_over_ranks(time.perf_counter() - t0)
+    sweep_s = 1e30
+    for _ in range(2):                                           # best of two: a single sweep right after the timed iterations is at the mercy of the power state
+        t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = min(sweep_s, max_over_ranks(time.perf_counter() - t0))
     lt = ctx.loglik()
     P = 1 << depth
     it_s = float(np.mean(ms)) * 1e-3
