@@ -42,11 +42,14 @@ __device__ __forceinline__ double chain_log_kernel(const float* nodes, long long
     return dim * lnk - 0.5 * s / (ks * ks);
 }
 
-template <bool SM>
+// COMPACT: the warp-cooperative increments phase for long trees ((P - 1) * dim >= 64 normals per hop); short trees keep the per-element loop — with the 30 increments of the
+// banana PMP the queue bookkeeping costs more than it saves (34.1 against 29.7 ms), with the 280 of N(0, I_40), binary D = 3, it is 21.9 against 34.3 ms.
+template <bool SM, bool COMPACT>
 __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
     extern __shared__ __align__(16) unsigned char chain_sm[];
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chains) return;
+    if (!COMPACT && c >= a.n_chains) return;
+    const bool live = COMPACT ? (c < a.n_chains) : true;   // COMPACT: threads past the last chain keep running, the increments phase is warp-cooperative
     const pmp_config& cfg = a.cfg;
     const int P = a.P, dim = cfg.dim;
     const long long nc = a.n_chains;
@@ -62,6 +65,10 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
     const bool use_kernel = !(cfg.flags & PMP_FLAG_NO_KERNEL_TERM);
     const int uniform = (cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0;
     const unsigned long long cbase = (unsigned long long)c << 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // tail quantiles of a warp's chains, evaluated 32 at a time (see propose_level_kernel): element, owner lane, uniform
+    __shared__ int q_e[COMPACT ? 4 : 1][COMPACT ? 96 : 1], q_o[COMPACT ? 4 : 1][COMPACT ? 96 : 1];
+    __shared__ double q_u[COMPACT ? 4 : 1][COMPACT ? 96 : 1];
     double* lt = work;
     double* A = work + (long long)P * sn;
     double* tmp = work + 2ll * P * sn;
@@ -70,15 +77,67 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
 
     for (int it = 0; it < a.iters; ++it) {
         const unsigned long long iter = a.iter0 + (unsigned long long)it;
-        // ---- tree nodes (parents precede children in index order for all three shapes)
-        for (int j = 0; j < dim; ++j) NODE(0, j) = a.states[(long long)j * nc + c];
-        for (int p = 1; p < P; ++p) {
+        // ---- tree nodes (parents precede children in index order for all three shapes).  Phase 1 leaves the increment fl(alpha z) of every element
+        // e = p * dim + j in its node slot: one Philox block per element PAIR, the quantile's central branch inline, its tail branch (15 % of the draws) queued
+        // per warp and evaluated with all lanes busy — the per-element loop made every warp run both branches for every normal (ncu r2m: the normals were
+        // half of the kernel's instructions).  Phase 2 adds the parents in index order: child = fl(parent + fl(alpha z)), the same bits.
+        if (live) for (int j = 0; j < dim; ++j) NODE(0, j) = a.states[(long long)j * nc + c];
+        if (!COMPACT) {
+            for (int p = 1; p < P; ++p) {
+                int parent = 0;
+                if (cfg.tree != PMP_TREE_FLAT) { long long s = 1; while ((long long)p >= s * b) s *= b; parent = (int)(p % s); }
+                for (int j = 0; j < dim; ++j) {
+                    float z = (float)stream_step(a.seed, iter, cbase | (unsigned long long)((long long)p * dim + j), uniform);
+                    NODE(p, j) = __fadd_rn(NODE(parent, j), __fmul_rn(cfg.alpha, z));
+                }
+            }
+        } else {
+            int qn = 0;
+            auto drain = [&](int count) {
+                const int x = qn - count + lane;
+                if (lane < count) {
+                    const int e = q_e[warp][x], ol = q_o[warp][x];
+                    const long long slot = SM ? (long long)(warp * 32 + ol) : (c - lane + ol);
+                    nodes[(long long)e * sn + slot] = __fmul_rn(cfg.alpha, (float)det_norm_ppf(q_u[warp][x]));
+                }
+                qn -= count;
+                __syncwarp();
+            };
+            const int e_hi = P * dim;
+            for (int k = dim >> 1; 2 * k < e_hi; ++k) {
+                double u[2]; bool tail[2] = {false, false};
+                if (live) {
+                    const unsigned long long blk = (cbase | (unsigned long long)(2 * k)) >> 1;
+                    uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)iter, ((uint32_t)(iter >> 32) & 0x00FFFFFFu) | (STREAM_PROPOSAL << 24)};
+                    philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                    u[0] = u64_to_open((uint64_t)ctr[1] << 32 | ctr[0]);
+                    u[1] = u64_to_open((uint64_t)ctr[3] << 32 | ctr[2]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int e = 2 * k + h;
+                        if (e < dim || e >= e_hi) continue;
+                        const double q = PMP_ADD(u[h], -0.5);
+                        if (fabs(q) <= 0.425) nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)ppf_central(q));
+                        else tail[h] = true;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned mask = __ballot_sync(0xffffffffu, tail[h]);
+                    if (tail[h]) { const int x = qn + __popc(mask & ((1u << lane) - 1u)); q_e[warp][x] = 2 * k + h; q_o[warp][x] = lane; q_u[warp][x] = u[h]; }
+                    qn += __popc(mask);
+                }
+                __syncwarp();
+                while (qn >= 32) drain(32);
+            }
+            if (qn > 0) drain(qn);
+            __syncwarp();
+        }
+        if (live) {
+        if (COMPACT) for (int p = 1; p < P; ++p) {
             int parent = 0;
             if (cfg.tree != PMP_TREE_FLAT) { long long s = 1; while ((long long)p >= s * b) s *= b; parent = (int)(p % s); }
-            for (int j = 0; j < dim; ++j) {
-                float z = (float)stream_step(a.seed, iter, cbase | (unsigned long long)((long long)p * dim + j), uniform);
-                NODE(p, j) = __fadd_rn(NODE(parent, j), __fmul_rn(cfg.alpha, z));
-            }
+            for (int j = 0; j < dim; ++j) NODE(p, j) = __fadd_rn(NODE(parent, j), NODE(p, j));
         }
         // ---- log-targets
         for (int p = 0; p < P; ++p) W(lt, p) = analytic_logtarget(cfg.target, &NODE(p, 0), (int)sn, dim, cfg.target_p0, cfg.target_p1) / (double)cfg.scale;
@@ -157,8 +216,18 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             for (int p = 0; p < P; ++p) { double w = exp(W(A, p) - mx); run += (w == w) ? w : 0.0; W(A, p) = run; }
             const double total = run;
             const bool right = (cfg.draw != PMP_DRAW_CUDA);
+            unsigned long long dw1 = 0ull;                 // draws 2m and 2m+1 are the two words of one Philox block
             for (int t = 0; t < n_draws; ++t) {
-                double thr = u64_to_unit(stream_u64(a.seed, iter, STREAM_DRAW, cbase | (unsigned long long)t)) * total;
+                unsigned long long word;
+                if (!COMPACT) word = stream_u64(a.seed, iter, STREAM_DRAW, cbase | (unsigned long long)t);
+                else if (t & 1) word = dw1;
+                else {
+                    const unsigned long long blk = (cbase | (unsigned long long)t) >> 1;
+                    uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)iter, ((uint32_t)(iter >> 32) & 0x00FFFFFFu) | (STREAM_DRAW << 24)};
+                    philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                    word = (unsigned long long)ctr[1] << 32 | ctr[0]; dw1 = (unsigned long long)ctr[3] << 32 | ctr[2];
+                }
+                double thr = u64_to_unit(word) * total;
                 int lo = 0, hi = P;
                 while (lo < hi) { int mid = (lo + hi) >> 1; double v = W(A, mid); bool go = right ? (v <= thr) : (v < thr); if (go) lo = mid + 1; else hi = mid; }
                 W(draws, t) = min(lo, P - 1);
@@ -177,6 +246,8 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             }
         }
         for (int j = 0; j < dim; ++j) a.states[(long long)j * nc + c] = NODE(next, j);
+        }   // live
+        __syncwarp();
     }
 #undef NODE
 #undef W
@@ -263,12 +334,20 @@ static int chains_launch(pmp_ctx* c, int64_t iters, int record) {
     int threads = 128;
     while (threads > 32 && per_chain * threads > 96 * 1024) threads >>= 1;
     const bool in_smem = per_chain * threads <= 96 * 1024 && !getenv("PMP_CHAINS_GLOBAL_SCRATCH");
+    const bool compact = !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) && (long long)(c->P - 1) * c->cfg.dim >= 64;
     if (in_smem) {
         const size_t smem = per_chain * threads;
         static size_t attr_set = 0;
-        if (smem > attr_set) { PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = 100 * 1024; }
-        chains_kernel<true><<<(unsigned)((c->n_chains + threads - 1) / threads), threads, smem, c->stream>>>(a);
-    } else chains_kernel<false><<<(unsigned)((c->n_chains + 127) / 128), 128, 0, c->stream>>>(a);
+        if (smem > attr_set) {
+            PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = 100 * 1024;
+        }
+        const unsigned grid = (unsigned)((c->n_chains + threads - 1) / threads);
+        if (compact) chains_kernel<true, true><<<grid, threads, smem, c->stream>>>(a);
+        else chains_kernel<true, false><<<grid, threads, smem, c->stream>>>(a);
+    } else if (compact) chains_kernel<false, true><<<(unsigned)((c->n_chains + 127) / 128), 128, 0, c->stream>>>(a);
+    else chains_kernel<false, false><<<(unsigned)((c->n_chains + 127) / 128), 128, 0, c->stream>>>(a);
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     c->chain_iteration += (unsigned long long)iters;
