@@ -1071,6 +1071,20 @@ __global__ void gather_bias_kernel(const float* __restrict__ theta, long long th
     out[i] = v;
 }
 
+// max_j,p |theta_p[j] - theta_0[j]| as the bit pattern of a non-negative float (unsigned order = float order): decides whether caller-supplied nodes are small
+// increments about node 0 and can take the one-product delta chain
+__global__ void fc_max_delta_kernel(const float* __restrict__ theta, long long dim, int P, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    const long long total = (long long)P * dim;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i % dim;
+        const float d = fabsf(theta[i] - theta[j]);
+        m = (d == d) ? fmaxf(m, d) : INFINITY;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 __global__ void finalize_loss_kernel(const unsigned long long* loss_fx, double* lt, int P, double n_global, double inv_scale) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) lt[p] = -((double)(long long)loss_fx[p] * (1.0 / 4294967296.0) / n_global) * inv_scale;   // -(mean CE)/loss_div
@@ -1415,6 +1429,20 @@ int pmp_fc_loglik(pmp_ctx* c) {
     // large steps) takes the 3-product split (v2).  PMP_FC_MODE=x3 | delta overrides.
     bool delta = s->version == 2 && !c->props_external && P > 1 &&
                  (double)c->cfg.alpha * sqrt((double)(c->cfg.tree == PMP_TREE_FLAT ? 1 : c->cfg.depth)) <= 1e-3;
+    if (s->version == 2 && c->props_external && P > 1 && !getenv("PMP_FC_MODE")) {
+        // caller-supplied nodes (the reference's step(s, proposal_nets, ...) call pattern, PMP_FC.py:105-143: its own update() moves every weight by N(0, 1e-4)): measure them
+        unsigned int* d_m = reinterpret_cast<unsigned int*>(s->loss + MAX_NODES - 1);          // last slot of the loss buffer: never a node's sum (P <= MAX_NODES - 1 here) — reset below
+        if (P <= MAX_NODES - 1) {
+            PMP_CUDA(cudaMemsetAsync(d_m, 0, sizeof(unsigned long long), c->stream));
+            fc_max_delta_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_props, THETA_DIM, P, d_m);
+            c->launches++;
+            unsigned int bits = 0;
+            PMP_CUDA(cudaMemcpyAsync(&bits, d_m, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+            PMP_CUDA(cudaStreamSynchronize(c->stream));
+            float mx; memcpy(&mx, &bits, sizeof(mx));
+            delta = mx <= 5e-3f;                           // the device proposals' bound alpha sqrt(depth) <= 1e-3 is a typical size; five of them is the largest increment
+        }
+    }
     if (const char* m = getenv("PMP_FC_MODE")) { if (!strcmp(m, "x3")) delta = false; else if (!strcmp(m, "delta") && s->version == 2) delta = true; }
     if (delta) {
         // TMA multicast over clusters of two CTA pairs (layers 1, 2): built, parity-green, and SLOWER — opt-in with PMP_FC_MCAST=1.  ncu (r2q): the bytes an

@@ -229,3 +229,27 @@ def test_fc_node_batch_size_does_not_change_a_bit(ctx, monkeypatch):
     assert np.array_equal(out["8"], out["20"]) and np.array_equal(out["8"], out["3"])
     truth = np.array([-o.fc_mean_ce_f64(X, y, ctx.read_proposals()[p]) / 10.0 for p in (0, 7, 31)])
     np.testing.assert_allclose(out["20"][[0, 7, 31]], truth, rtol=2e-5)
+
+
+def test_fc_caller_supplied_small_increments_take_the_delta_chain(ctx):
+    """the reference's step(s, proposal_nets, ...) hands over its own proposals (PMP_FC.py:105-143); when they are small increments about node 0 the library measures that
+    and runs the same one-product delta chain as for its own proposals (identical bits); unrelated parameter vectors keep the 3-product split"""
+    import os
+    from conftest import ROOT
+    from oracle import oracle as o
+    from pmp_mcmc_b200 import _lib as L
+    theta0 = np.load(os.path.join(ROOT, "tests", "golden", "fc_theta0.npy"))
+    X, y = _data(900, seed=4)
+    ctx.configure(L.TREE_BINARY, depth=3, dim=o.FC_DIM, target=L.TARGET_FC, algo=L.ALGO_PSP, draw=L.DRAW_SINGLE, flags=L.FLAG_STANDARDIZE, alpha=1e-4, scale=10.0)
+    ctx.set_data_fc(X, y); ctx.set_state(theta0); ctx.seed(3, 0); ctx.propose()
+    props = ctx.read_proposals()
+    lt_dev = ctx.loglik()
+    ctx.write_proposals(props)
+    lt_ext = ctx.loglik()
+    assert np.array_equal(lt_dev, lt_ext)
+    far = props.copy(); far[5] = o.fc_init_theta(3)                      # one unrelated node: the whole sweep falls back to the split
+    ctx.write_proposals(far)
+    lt_far = ctx.loglik()
+    truth = np.array([-o.fc_mean_ce_f64(X, y, far[p]) / 10.0 for p in (0, 3, 5)])
+    np.testing.assert_allclose(lt_far[[0, 3, 5]], truth, rtol=2e-5)
+    np.testing.assert_allclose(lt_far[[0, 3]], lt_dev[[0, 3]], rtol=2e-6)
