@@ -19,39 +19,71 @@ constexpr uint32_t STREAM_MOMENTUM = 4;
 constexpr int HMC_THREADS = 256;
 constexpr int HMC_MAX_P = 1024;             // nodes of an HMC tree / path (the reference runs 2 .. 32)
 
-// p0 = scale * N(0,1) (or injected); kinetic energy of p0; p = p0 + sign * step * grad / 2; theta_child = theta_parent + sign * step * p
-__global__ void hmc_begin_kernel(const float* __restrict__ theta_parent, const float* __restrict__ grad, float* __restrict__ theta_child, float* p_out,
-                                 const float* p_init /* may alias p_out: the MP path carries one momentum buffer from node to node */, long long dim, float step, float sign, float p_scale, uint64_t seed, uint64_t iter, uint64_t idx0,
-                                 double* __restrict__ ke) {
-    double k = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
-        const float p0 = p_init ? p_init[i] : __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + (uint64_t)i), p_scale);
-        k += (double)p0 * (double)p0;
-        // the reference's float32 operation order: p += step * du_dx / 2 ; par += step * p   (cifar_PMPhmc.py:141-147, cifar_MPhmc.py:119-125)
-        const float p = __fadd_rn(p0, __fdiv_rn(__fmul_rn(sign * step, grad[i]), 2.0f));
-        p_out[i] = p;
-        theta_child[i] = __fadd_rn(theta_parent[i], __fmul_rn(sign * step, p));
-    }
+// p0 = scale * N(0,1) (or injected); kinetic energy of p0; p = p0 + sign * step * grad / 2; theta_child = theta_parent + sign * step * p.
+// Elementwise and HBM-bound: 16-byte accesses, four elements per thread and trip (a scalar tail when dim is not a multiple of 4 or a pointer is not 16-byte aligned).
+__device__ __forceinline__ void hmc_begin_elem(float th, float g, float p0, float ss, float& p, float& child, double& k) {
+    k += (double)p0 * (double)p0;
+    // the reference's float32 operation order: p += step * du_dx / 2 ; par += step * p   (cifar_PMPhmc.py:141-147, cifar_MPhmc.py:119-125)
+    p = __fadd_rn(p0, __fdiv_rn(__fmul_rn(ss, g), 2.0f));
+    child = __fadd_rn(th, __fmul_rn(ss, p));
+}
+__device__ __forceinline__ void hmc_block_sum(double k, double* dst) {
     __shared__ double red[HMC_THREADS / 32];
     for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
     __syncthreads();
-    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < HMC_THREADS / 32; ++w) s += red[w]; atomicAdd(ke, 0.5 * s); }
+    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < HMC_THREADS / 32; ++w) s += red[w]; atomicAdd(dst, 0.5 * s); }
+}
+__global__ void hmc_begin_kernel(const float* __restrict__ theta_parent, const float* __restrict__ grad, float* __restrict__ theta_child, float* p_out,
+                                 const float* p_init /* may alias p_out: the MP path carries one momentum buffer from node to node */, long long dim, float step, float sign,
+                                 float p_scale, uint64_t seed, uint64_t iter, uint64_t idx0, double* __restrict__ ke, int vec) {
+    double k = 0.0;
+    const float ss = sign * step;
+    const long long n4 = vec ? dim / 4 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 th = __ldg(reinterpret_cast<const float4*>(theta_parent) + i), g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+        float4 p0;
+        if (p_init) p0 = reinterpret_cast<const float4*>(p_init)[i];
+        else {
+            p0.x = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i), p_scale);
+            p0.y = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i + 1), p_scale);
+            p0.z = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i + 2), p_scale);
+            p0.w = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i + 3), p_scale);
+        }
+        float4 p, ch;
+        hmc_begin_elem(th.x, g.x, p0.x, ss, p.x, ch.x, k); hmc_begin_elem(th.y, g.y, p0.y, ss, p.y, ch.y, k);
+        hmc_begin_elem(th.z, g.z, p0.z, ss, p.z, ch.z, k); hmc_begin_elem(th.w, g.w, p0.w, ss, p.w, ch.w, k);
+        reinterpret_cast<float4*>(p_out)[i] = p;
+        reinterpret_cast<float4*>(theta_child)[i] = ch;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
+        const float p0 = p_init ? p_init[i] : __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + (uint64_t)i), p_scale);
+        float p, ch;
+        hmc_begin_elem(theta_parent[i], grad[i], p0, ss, p, ch, k);
+        p_out[i] = p; theta_child[i] = ch;
+    }
+    hmc_block_sum(k, ke);
 }
 
 // p += sign * step * grad / 2; kinetic energy of the final momentum
-__global__ void hmc_end_kernel(float* __restrict__ p, const float* __restrict__ grad, long long dim, float step, float sign, double* __restrict__ ke) {
+__global__ void hmc_end_kernel(float* __restrict__ p, const float* __restrict__ grad, long long dim, float step, float sign, double* __restrict__ ke, int vec) {
     double k = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
-        const float q = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(sign * step, grad[i]), 2.0f));
+    const float ss = sign * step;
+    const long long n4 = vec ? dim / 4 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 q = reinterpret_cast<float4*>(p)[i];
+        const float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+        q.x = __fadd_rn(q.x, __fdiv_rn(__fmul_rn(ss, g.x), 2.0f)); q.y = __fadd_rn(q.y, __fdiv_rn(__fmul_rn(ss, g.y), 2.0f));
+        q.z = __fadd_rn(q.z, __fdiv_rn(__fmul_rn(ss, g.z), 2.0f)); q.w = __fadd_rn(q.w, __fdiv_rn(__fmul_rn(ss, g.w), 2.0f));
+        reinterpret_cast<float4*>(p)[i] = q;
+        k += (double)q.x * (double)q.x + (double)q.y * (double)q.y + (double)q.z * (double)q.z + (double)q.w * (double)q.w;
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += (long long)gridDim.x * blockDim.x) {
+        const float q = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(ss, grad[i]), 2.0f));
         p[i] = q;
         k += (double)q * (double)q;
     }
-    __shared__ double red[HMC_THREADS / 32];
-    for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = k;
-    __syncthreads();
-    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < HMC_THREADS / 32; ++w) s += red[w]; atomicAdd(ke + 1, 0.5 * s); }
+    hmc_block_sum(k, ke + 1);
 }
 
 struct HmcAcceptArgs {
@@ -141,10 +173,11 @@ int pmp_hmc_leapfrog_begin(pmp_ctx* c, const float* theta_parent, const float* g
     if ((rc = hmc_scratch(c))) return rc;
     double* ke = reinterpret_cast<double*>(c->d_hmc);
     PMP_CUDA(cudaMemsetAsync(ke, 0, 2 * sizeof(double), c->stream));
-    long long blocks = (dim + HMC_THREADS - 1) / HMC_THREADS;
-    if (blocks > 8ll * c->sm_count) blocks = 8ll * c->sm_count;
+    long long blocks = (dim / 4 + HMC_THREADS - 1) / HMC_THREADS + 1;
+    if (blocks > 16ll * c->sm_count) blocks = 16ll * c->sm_count;
+    const int vec = (((uintptr_t)theta_parent | (uintptr_t)grad_parent | (uintptr_t)theta_child | (uintptr_t)p_child | (uintptr_t)p_init) & 15) == 0;
     hmc_begin_kernel<<<(unsigned)blocks, HMC_THREADS, 0, c->stream>>>(theta_parent, grad_parent, theta_child, p_child, p_init, dim, step, sign, p_scale,
-                                                                       c->seed, c->host_iter, stream_index * (uint64_t)dim, ke);
+                                                                       c->seed, c->host_iter, stream_index * (uint64_t)dim, ke, vec);
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     PMP_CUDA(cudaMemcpyAsync(ke_init, ke, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -159,9 +192,10 @@ int pmp_hmc_leapfrog_end(pmp_ctx* c, float* p_child, const float* grad_child, in
     if ((rc = hmc_scratch(c))) return rc;
     double* ke = reinterpret_cast<double*>(c->d_hmc);
     PMP_CUDA(cudaMemsetAsync(ke + 1, 0, sizeof(double), c->stream));
-    long long blocks = (dim + HMC_THREADS - 1) / HMC_THREADS;
-    if (blocks > 8ll * c->sm_count) blocks = 8ll * c->sm_count;
-    hmc_end_kernel<<<(unsigned)blocks, HMC_THREADS, 0, c->stream>>>(p_child, grad_child, dim, step, sign, ke);
+    long long blocks = (dim / 4 + HMC_THREADS - 1) / HMC_THREADS + 1;
+    if (blocks > 16ll * c->sm_count) blocks = 16ll * c->sm_count;
+    const int vec = (((uintptr_t)p_child | (uintptr_t)grad_child) & 15) == 0;
+    hmc_end_kernel<<<(unsigned)blocks, HMC_THREADS, 0, c->stream>>>(p_child, grad_child, dim, step, sign, ke, vec);
     c->launches++;
     PMP_CUDA(cudaGetLastError());
     PMP_CUDA(cudaMemcpyAsync(ke_final, ke + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
