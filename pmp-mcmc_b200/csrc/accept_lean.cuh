@@ -67,13 +67,19 @@ struct LeanRegs {
 // One buffer of nodes suffices: the nodes of it + 1 are written after every sweep CTA has arrived for it, i.e. after it has read the
 // nodes of it.  Two halves of normals: a sweep CTA writes the normals of it + 1 (half (it + 1) & 1) at the start of its sweep it, which it
 // can only enter after the acceptance of it - 1 — the reader of the other half — has published its nodes.
+//   state  (flat trees, chain_persistent_kernel only) the accepted state {b0 | tag}, {b1 | tag}, {sigma | tag}: with a flat tree a node is
+//          state + alpha * z(node), and z depends on counters only, so every sweep CTA derives its own tile's nodes from these three words
+//          and the normals it computed while it waited — the acceptance publishes 24 bytes instead of generating and storing P nodes on the
+//          critical path, and the sweep CTAs save the second L2 round trip of fetch_node.
 struct Handoff {
     unsigned long long* nodes;
     unsigned long long* zt;
     unsigned int epoch;
+    unsigned long long* state;
 };
 __host__ __device__ inline size_t handoff_node_words(int P) { return (size_t)P * 4; }
 __host__ __device__ inline size_t handoff_z_words(int P) { return (size_t)2 * 3 * P; }
+__host__ __device__ inline size_t handoff_state_words() { return 4; }
 
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void st_relaxed_gpu_v2(unsigned long long* p, unsigned long long a, unsigned long long b) { asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory"); }
@@ -97,10 +103,42 @@ __device__ __forceinline__ float proposal_value_zs(const ProposeArgs& a, const f
 // loop: it is complete before this kernel starts).  TABLE_CRIT: the table the sweep CTAs of the same persistent kernel fill
 // during the sweep — complete only once they have all arrived, so it is read at the start of the critical phase, in the
 // same L2 round trip as the sums.  GENERATE: computed here (3P quantile evaluations in binary64 on one SM: slow).
-enum { LEAN_Z_TABLE_PRE = 0, LEAN_Z_GENERATE = 1, LEAN_Z_TABLE_CRIT = 2 };
+// HS_PRE: the tagged table of the flag-in-data hand-offs, read in the pre phase (a tagged word is complete by itself, so the read need not wait for the
+// arrivals: it spins until the sweep CTAs' side job has written it, which depends on nothing this CTA still has to do).  DERIVE: flat trees in
+// chain_persistent_kernel — the critical phase publishes the accepted state only; the nodes are derived from it by their readers (the sweep CTAs, and
+// lean_derive_props here, off the critical path).
+enum { LEAN_Z_TABLE_PRE = 0, LEAN_Z_GENERATE = 1, LEAN_Z_TABLE_CRIT = 2, LEAN_Z_HS_PRE = 3, LEAN_Z_DERIVE = 4 };
+
+// tagged normals -> s.z (spins until every word carries `tag`)
+__device__ __forceinline__ void lean_read_tagged_z(const LeanSmem& s, const unsigned long long* zn, int P, unsigned long long tag) {
+    const int tid = threadIdx.x;
+    unsigned long long zw[3 * LEAN_K];
+#pragma unroll
+    for (int k = 0; k < 3 * LEAN_K; ++k) { const int g = tid + k * ACCEPT_THREADS; zw[k] = (g < 3 * P) ? ld_relaxed_gpu_u64(zn + g) : tag; }
+#pragma unroll
+    for (int k = 0; k < 3 * LEAN_K; ++k) {
+        const int g = tid + k * ACCEPT_THREADS;
+        if (g < 3 * P) { SpinGuard sg; while (!hs_tag_ok(zw[k], tag)) { sg.tick(); zw[k] = ld_relaxed_gpu_u64(zn + g); } s.z[g] = __uint_as_float((unsigned)zw[k]); }
+    }
+}
+
+// DERIVE: the nodes of iteration `iter` from the state the previous critical phase accepted (r.n0..n2) and the tagged normals of `iter`, into shared memory and
+// into the plain copy in global memory (host reads, first iteration of the next launch).  Same expression as proposal_value_zs for a flat tree.
+__device__ __forceinline__ void lean_derive_props(const AcceptFastArgs& fa, const LeanSmem& s, const LeanRegs& r, const Handoff& hs, unsigned long long iter, unsigned long long tag) {
+    const int P = fa.base.P, tid = threadIdx.x;
+    lean_read_tagged_z(s, hs.zt + (iter & 1) * (long long)(P * 3), P, tag);
+    float* props_out = const_cast<float*>(fa.base.props);
+    for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) {      // thread g reads the s.z[g] it wrote itself
+        const int node = g / 3, j = g - 3 * node;
+        float v = j == 0 ? r.n0 : (j == 1 ? r.n1 : r.n2);
+        if (node > 0) v = __fadd_rn(v, __fmul_rn(fa.gen.alpha, s.z[g]));
+        s.props[g] = v; props_out[g] = v;
+    }
+}
 
 template <int ALGO>
-__device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], int* s_pick, int z_mode) {
+__device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSmem& s, LeanRegs& r, double (*red)[32], int* s_pick, int z_mode,
+                                         const Handoff* hs = nullptr, unsigned long long tag = 0, bool first = true) {
     const AcceptArgs& a = fa.base;
     const pmp_config& cfg = a.cfg;
     const int P = a.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,9 +152,11 @@ __device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSme
         if (cfg.draw == PMP_DRAW_PYTHON) up = a.uniforms ? a.uniforms[P] : u64_to_unit(stream_u64(a.seed, r.iter, STREAM_PICK, 0));
         *s_pick = min(P - 1, (int)(up * (double)P));
     }
-    for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.props[g] = __ldcg(a.props + g);
+    if (z_mode == LEAN_Z_DERIVE && !first) lean_derive_props(fa, s, r, *hs, r.iter, tag);
+    else for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.props[g] = __ldcg(a.props + g);
     if (fa.make_next) {
-        if (z_mode == LEAN_Z_GENERATE) for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = (float)stream_step(fa.gen.seed, r.iter + 1, (unsigned long long)g, fa.gen.uniform);
+        if (z_mode == LEAN_Z_HS_PRE) lean_read_tagged_z(s, hs->zt + ((r.iter + 1) & 1) * (long long)(P * 3), P, tag);
+        else if (z_mode == LEAN_Z_GENERATE) for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = (float)stream_step(fa.gen.seed, r.iter + 1, (unsigned long long)g, fa.gen.uniform);
         else if (z_mode == LEAN_Z_TABLE_PRE) { const float* zn = fa.z + ((r.iter + 1) & 1) * (long long)(P * 3); for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) s.z[g] = __ldcg(zn + g); }
     }
 #pragma unroll
@@ -186,16 +226,10 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
     unsigned long long q[LEAN_K];
 #pragma unroll
     for (int k = 0; k < LEAN_K; ++k) { const int p = tid + k * ACCEPT_THREADS; q[k] = (p < P) ? (qin ? qin[k] : __ldcg(a.acc + p)) : 0ull; }
-    if (hs && fa.make_next) {                                 // tagged normals: written by the sweep CTAs' side job at the start of their sweep — long since there
-        const unsigned long long* zn = hs->zt + ((r.iter + 1) & 1) * (long long)(P * 3);
-        unsigned long long zw[3 * LEAN_K];
-#pragma unroll
-        for (int k = 0; k < 3 * LEAN_K; ++k) { const int g = tid + k * ACCEPT_THREADS; zw[k] = (g < 3 * P) ? ld_relaxed_gpu_u64(zn + g) : tag; }
-#pragma unroll
-        for (int k = 0; k < 3 * LEAN_K; ++k) {
-            const int g = tid + k * ACCEPT_THREADS;
-            if (g < 3 * P) { SpinGuard sg; while (!hs_tag_ok(zw[k], tag)) { sg.tick(); zw[k] = ld_relaxed_gpu_u64(zn + g); } s.z[g] = __uint_as_float((unsigned)zw[k]); }
-        }
+    if (z_mode == LEAN_Z_HS_PRE || z_mode == LEAN_Z_DERIVE) {
+        // the normals were read in the pre phase / are not needed here
+    } else if (hs && fa.make_next) {                          // tagged normals: written by the sweep CTAs' side job at the start of their sweep — long since there
+        lean_read_tagged_z(s, hs->zt + ((r.iter + 1) & 1) * (long long)(P * 3), P, tag);
     } else if (z_mode == LEAN_Z_TABLE_CRIT && fa.make_next) {       // same L2 round trip as the sums; first read after the block barriers below
         const float* zn = fa.z + ((r.iter + 1) & 1) * (long long)(P * 3);
         float zr[3 * LEAN_K];
@@ -287,7 +321,15 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
                 const bool g2 = 32 + lane < S && i2 < P && (right ? (s.A[i2] <= thr) : (s.A[i2] < thr));
                 cnt = base + __popc(__ballot_sync(0xffffffffu, g1)) + __popc(__ballot_sync(0xffffffffu, g2));
             }
-            if (lane == 0) red[2][0] = (double)min(cnt, P - 1);
+            if (lane == 0) {
+                const int nx = min(cnt, P - 1);
+                red[2][0] = (double)nx;
+                if (z_mode == LEAN_Z_DERIVE && a.advance) {          // what the sweep CTAs wait for: 24 bytes
+                    const unsigned long long tn = tag + (1ull << 32);
+                    st_relaxed_gpu_v2(hs->state, (unsigned long long)__float_as_uint(s.props[3 * nx]) | tn, (unsigned long long)__float_as_uint(s.props[3 * nx + 1]) | tn);
+                    st_relaxed_gpu_u64(hs->state + 2, (unsigned long long)__float_as_uint(s.props[3 * nx + 2]) | tn);
+                }
+            }
         }
     }
     __syncthreads();
@@ -297,7 +339,7 @@ __device__ __forceinline__ void lean_crit(const AcceptFastArgs& fa, const LeanSm
 
     // ---- what the next sweep waits for: its nodes and the iteration counter ------------------------------------------------
     if (a.advance) {
-        if (fa.make_next) {
+        if (fa.make_next && z_mode != LEAN_Z_DERIVE) {
             float* props_out = const_cast<float*>(a.props);
             const unsigned long long tag_next = tag + (1ull << 32);
             for (int g = tid; g < P * 3; g += ACCEPT_THREADS) {

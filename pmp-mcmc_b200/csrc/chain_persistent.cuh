@@ -34,6 +34,7 @@ struct PersistArgs {
     int iters;
     int max_chunks;          // chunks per sweep CTA that fit the dynamic shared memory
     Handoff hs;              // HS kernels: flag-in-data hand-offs (accept_lean.cuh)
+    int derive;              // HS, flat tree, one segment per sweep CTA: the acceptance publishes the accepted state only and every reader derives its nodes (Handoff::state)
 };
 
 // A sweep CTA's thread i < PERSIST_PT fetches node (node_base + i) of iteration `it`: plain memory for the first iteration of a launch
@@ -110,13 +111,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
         __shared__ int s_pick;
         const LeanSmem ls = lean_carve(dsm, pa.fa.base.P, ALGO);
         LeanRegs lr;
+        const int zm = !HS ? LEAN_Z_TABLE_CRIT : (pa.derive ? LEAN_Z_DERIVE : LEAN_Z_HS_PRE);
         for (int it = 0; it < pa.iters; ++it) {
-            lean_pre<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
+            lean_pre<ALGO>(pa.fa, ls, lr, red, &s_pick, zm, &pa.hs, (unsigned long long)(pa.hs.epoch + (unsigned)it + 1u) << 32, it == 0);
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 8] = clock64(); pa.fa.base.dbg[32 + 24] = globaltimer_ns(); }
             if (tid == 0) spin_until_ge(&pa.sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
             __syncthreads();
             if (HS) {       // the next nodes and normals travel as tagged words: no fence, no version counter
-                lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT, nullptr, &pa.hs, (unsigned long long)(pa.hs.epoch + (unsigned)it + 1u) << 32);
+                lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, zm, nullptr, &pa.hs, (unsigned long long)(pa.hs.epoch + (unsigned)it + 1u) << 32);
                 __syncthreads();
             } else {
                 lean_crit<ALGO>(pa.fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
@@ -129,6 +131,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
             __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre / by the host
             __syncthreads();
         }
+        if (HS && pa.derive && pa.iters > 0) {      // the nodes of the iteration after the last one: the plain copy the host and the next launch read
+            lean_derive_props(pa.fa, ls, lr, pa.hs, lr.iter + 1, (unsigned long long)(pa.hs.epoch + (unsigned)pa.iters + 1u) << 32);
+            __threadfence();
+        }
         return;
     }
 
@@ -139,6 +145,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE);   // [TD][PT]
     __shared__ float sprops[PT * 3];
     __shared__ double sscl[PT];
+    __shared__ float saz[PT * 3];            // derive: alpha * z of this CTA's tile for the coming iteration
+    __shared__ float s_state[4];
 
     const int tp = tid & (TP - 1), td = tid / TP;
     const int ntiles = (a.P + PT - 1) / PT;
@@ -178,7 +186,19 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
             __syncthreads();
         }
         PMP_STAMP(dbg, 1);
-        {   // side job: this CTA's slice of the NEXT iteration's normals (they depend on counters only); read by the acceptance CTA
+        if (HS && pa.derive) {
+            // this tile's nodes = accepted state + alpha * z(it): the normals depend on counters only and were computed after the previous arrival (below),
+            // while the acceptance was running; wait for the 24-byte state, then build the nodes from shared memory
+            if (it > 0) {
+                if (tid == 0) {
+                    unsigned long long w0, w1, w2;
+                    SpinGuard sg;
+                    for (;;) { ld_relaxed_gpu_v2(pa.hs.state, w0, w1); w2 = ld_relaxed_gpu_u64(pa.hs.state + 2); if (hs_tag_ok(w0, tag) && hs_tag_ok(w1, tag) && hs_tag_ok(w2, tag)) break; sg.tick(); }
+                    s_state[0] = __uint_as_float((unsigned)w0); s_state[1] = __uint_as_float((unsigned)w1); s_state[2] = __uint_as_float((unsigned)w2);
+                }
+                __syncthreads();
+            }
+        } else {   // side job: this CTA's slice of the NEXT iteration's normals (they depend on counters only); read by the acceptance CTA
             const int zcount = a.P * 3, per = (zcount + n_sweep - 1) / n_sweep;
             const unsigned long long iter = iter0 + (unsigned long long)it;
             for (int k = PERSIST_THREADS - 1 - tid; k < per; k += PERSIST_THREADS) {
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
                 }
             }
         }
-        if (HS && it > 0) {                   // (a CTA without units waits too: its normals of it + 2 would overwrite a half still in use)
+        if (HS && !pa.derive && it > 0) {     // (a CTA without units waits too: its normals of it + 2 would overwrite a half still in use)
             if (tid == 0) wait_nodes_hint(pa.hs, a.P, tag);
             __syncthreads();
         }
@@ -199,6 +219,12 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
             if (HS) {
                 if (tid < PT) {
                     float v0, v1, v2;
+                    if (pa.derive && it > 0) {
+                        const int node = node_base + tid;
+                        v0 = s_state[0]; v1 = s_state[1]; v2 = s_state[2];
+                        if (node >= a.P) { v0 = 0.f; v1 = 0.f; v2 = 0.f; }
+                        else if (node > 0) { v0 = __fadd_rn(v0, saz[3 * tid]); v1 = __fadd_rn(v1, saz[3 * tid + 1]); v2 = __fadd_rn(v2, saz[3 * tid + 2]); }
+                    } else
                     fetch_node(pa.hs, a.theta, node_base + tid, a.P, it == 0, tag, v0, v1, v2);
                     sprops[3 * tid] = v0; sprops[3 * tid + 1] = v1; sprops[3 * tid + 2] = v2;
                     sscl[tid] = (node_base + tid < a.P) ? (double)(1 << FX_SHIFT) / ((double)v2 * (double)v2) : 0.0;
@@ -245,6 +271,21 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
         __syncthreads();
         if (tid == 0) atomicAdd(&pa.sync->arrive, 1u);
         PMP_STAMP(dbg, 5);
+        if (HS && pa.derive && nseg == 1) {
+            // while the acceptance runs: the normals of the NEXT iteration's nodes of this tile (every CTA of a tile computes them for itself; the
+            // tile's first CTA also hands them to the acceptance CTA, which needs all nodes for its own pre phase — off the critical path)
+            const unsigned long long iter = iter0 + (unsigned long long)it + 1;
+            const bool publish = seg_c0[0] == 0;
+            const int zcount = a.P * 3;
+            for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {
+                const int e = seg_tile[0] * PT * 3 + i;
+                if (e < zcount) {
+                    const float zv = (float)stream_step(a.gen.seed, iter, (unsigned long long)e, a.gen.uniform);
+                    saz[i] = __fmul_rn(a.gen.alpha, zv);
+                    if (publish) st_relaxed_gpu_u64(pa.hs.zt + (iter & 1) * (long long)zcount + e, (unsigned long long)__float_as_uint(zv) | (tag + (1ull << 32)));
+                }
+            }
+        }
     }
     if (saturated) atomicOr(&a.cnt->flags, 1);
 }

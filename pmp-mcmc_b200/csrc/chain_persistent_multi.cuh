@@ -103,6 +103,8 @@ struct PersistMultiArgs {
     int iters;
     int max_chunks;
     int n_accept;              // acceptance CTAs (default: one per chain)
+    int derive;                // one chain, flat tree, HS: the acceptance publishes the accepted state only (Handoff::state; see chain_persistent_kernel).  Not used for
+                               // co-scheduled chains: there the sweep SMs have no idle time in which the tile's normals would come for free
 };
 
 template <int NG>
@@ -132,13 +134,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
         for (int it = 0; it < pa.iters; ++it) {
             for (int c = (int)blockIdx.x - n_sweep; c < K; c += n_accept) {
                 const AcceptFastArgs& fa = pa.ch[c].fa;
-                lean_pre<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
+                const int zm = (HS && pa.derive) ? LEAN_Z_DERIVE : LEAN_Z_TABLE_CRIT;
+                lean_pre<ALGO>(fa, ls, lr, red, &s_pick, zm, &pa.ch[c].hs, (unsigned long long)(pa.ch[c].hs.epoch + (unsigned)it + 1u) << 32, it == 0);
                 if (tid == 0) spin_until_ge(&pa.ch[c].sync->arrive, (unsigned)(it + 1) * (unsigned)n_sweep);
                 __syncthreads();
                 if (pa.ch[c].xchg.world > 1) peer_allreduce_acc(pa.ch[c].xchg, fa.base.acc, fa.base.P, it);
                 if (HS) {
                     const Handoff& hs = pa.ch[c].hs;
-                    lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT, nullptr, &hs, (unsigned long long)(hs.epoch + (unsigned)it + 1u) << 32);
+                    lean_crit<ALGO>(fa, ls, lr, red, &s_pick, zm, nullptr, &hs, (unsigned long long)(hs.epoch + (unsigned)it + 1u) << 32);
                     __syncthreads();
                 } else {
                     lean_crit<ALGO>(fa, ls, lr, red, &s_pick, LEAN_Z_TABLE_CRIT);
@@ -150,6 +153,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre of this chain / by the host
                 __syncthreads();
             }
+        }
+        if (HS && pa.derive && pa.iters > 0 && (int)blockIdx.x == n_sweep) {      // (derive: one chain) the nodes of the iteration after the last one
+            lean_derive_props(pa.ch[0].fa, ls, lr, pa.ch[0].hs, lr.iter + 1, (unsigned long long)(pa.ch[0].hs.epoch + (unsigned)pa.iters + 1u) << 32);
+            __threadfence();
         }
         return;
     }
@@ -163,10 +170,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
     unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE) + (size_t)half * TDH * PT;   // [TDH][PT] per half
     __shared__ float sprops_all[NG][PT * 3];
     __shared__ double sscl_all[NG][PT];
+    __shared__ float saz_all[NG][PT * 3];                        // derive: alpha * z of this CTA's tile for the coming iteration
+    __shared__ float s_state_all[NG][4];
     __shared__ unsigned long long s_iter0[PERSIST_MAX_CHAINS];   // Philox iteration of every chain at launch, read before any acceptance can advance it
     if (tid < K) s_iter0[tid] = __ldcg(&pa.ch[tid].sw.cnt->iteration);
     float* sprops = sprops_all[half];
     double* sscl = sscl_all[half];
+    float* saz = saz_all[half];
+    float* s_state = s_state_all[half];
 
     const int tp = htid & (TP - 1), td = htid / TP;
     const int P = a0.P;
@@ -209,7 +220,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 if (htid == 0 && it > 0) spin_until_ge(&pa.ch[c].sync->version, (unsigned)it);
                 group_sync<NG>(half);
             }
-            {   // side job: this CTA's slice of the chain's NEXT-iteration normals (they depend on counters only)
+            if (HS && pa.derive) {          // as in chain_persistent_kernel: wait for the 24-byte state; the tile's normals were computed after the previous arrival
+                if (it > 0) {
+                    if (htid == 0) {
+                        unsigned long long w0, w1, w2;
+                        SpinGuard sg;
+                        for (;;) { ld_relaxed_gpu_v2(hs.state, w0, w1); w2 = ld_relaxed_gpu_u64(hs.state + 2); if (hs_tag_ok(w0, tag) && hs_tag_ok(w1, tag) && hs_tag_ok(w2, tag)) break; sg.tick(); }
+                        s_state[0] = __uint_as_float((unsigned)w0); s_state[1] = __uint_as_float((unsigned)w1); s_state[2] = __uint_as_float((unsigned)w2);
+                    }
+                    group_sync<NG>(half);
+                }
+            } else {   // side job: this CTA's slice of the chain's NEXT-iteration normals (they depend on counters only)
                 const int zcount = P * 3, per = (zcount + n_sweep - 1) / n_sweep;
                 const unsigned long long iter = s_iter0[c] + (unsigned long long)it;
                 for (int k = HT - 1 - htid; k < per; k += HT) {
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                     }
                 }
             }
-            if (HS && it > 0) {                   // one thread per group waits for the chain's nodes (cheap hint, back-off); CTAs without units wait too
+            if (HS && !pa.derive && it > 0) {     // one thread per group waits for the chain's nodes (cheap hint, back-off); CTAs without units wait too
                 if (htid == 0) wait_nodes_hint(hs, P, tag);
                 group_sync<NG>(half);
             }
@@ -231,6 +252,12 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                 if (HS) {
                     for (int i = htid; i < PT; i += HT) {
                         float v0, v1, v2;
+                        if (pa.derive && it > 0) {
+                            const int node = node_base + i;
+                            v0 = s_state[0]; v1 = s_state[1]; v2 = s_state[2];
+                            if (node >= P) { v0 = 0.f; v1 = 0.f; v2 = 0.f; }
+                            else if (node > 0) { v0 = __fadd_rn(v0, saz[3 * i]); v1 = __fadd_rn(v1, saz[3 * i + 1]); v2 = __fadd_rn(v2, saz[3 * i + 2]); }
+                        } else
                         fetch_node(hs, a.theta, node_base + i, P, it == 0, tag, v0, v1, v2);
                         sprops[3 * i] = v0; sprops[3 * i + 1] = v1; sprops[3 * i + 2] = v2;
                         sscl[i] = (node_base + i < P) ? (double)(1 << FX_SHIFT) / ((double)v2 * (double)v2) : 0.0;
@@ -274,6 +301,19 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
             __threadfence();
             group_sync<NG>(half);
             if (htid == 0) atomicAdd(&pa.ch[c].sync->arrive, 1u);
+            if (HS && pa.derive && nseg == 1) {      // while the acceptance (and the cross-GPU exchange) runs: the normals of this tile's nodes of the next iteration
+                const unsigned long long iter = s_iter0[c] + (unsigned long long)it + 1;
+                const bool publish = seg_c0[0] == 0;
+                const int zcount = P * 3;
+                for (int i = htid; i < PT * 3; i += HT) {
+                    const int e = seg_tile[0] * PT * 3 + i;
+                    if (e < zcount) {
+                        const float zv = (float)stream_step(a.gen.seed, iter, (unsigned long long)e, a.gen.uniform);
+                        saz[i] = __fmul_rn(a.gen.alpha, zv);
+                        if (publish) st_relaxed_gpu_u64(hs.zt + (iter & 1) * (long long)zcount + e, (unsigned long long)__float_as_uint(zv) | (tag + (1ull << 32)));
+                    }
+                }
+            }
         }
     }
     for (int c = 0; c < K; ++c) if (sat_mask & (1u << c)) atomicOr(&pa.ch[c].sw.cnt->flags, 1);

@@ -741,14 +741,14 @@ int pmp_read_trace(pmp_ctx* c, int64_t max_iters, float* state, int32_t* next, i
 
 // Hand-off buffers of the persistent kernels (zeroed once: tag 0 is never current).
 static int ensure_handoff(pmp_ctx* c, Handoff* out) {
-    const size_t nw = handoff_node_words(c->P), zw = handoff_z_words(c->P);
+    const size_t nw = handoff_node_words(c->P), zw = handoff_z_words(c->P), sw = handoff_state_words();
     if (!c->d_hs || c->hs_P != c->P) {
         if (c->d_hs) { PMP_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->d_hs); c->d_hs = nullptr; }
-        PMP_CUDA(cudaMalloc((void**)&c->d_hs, (nw + zw) * sizeof(unsigned long long)));
-        PMP_CUDA(cudaMemsetAsync(c->d_hs, 0, (nw + zw) * sizeof(unsigned long long), c->stream));
-        c->hs_words = nw + zw; c->hs_P = c->P;
+        PMP_CUDA(cudaMalloc((void**)&c->d_hs, (nw + zw + sw) * sizeof(unsigned long long)));
+        PMP_CUDA(cudaMemsetAsync(c->d_hs, 0, (nw + zw + sw) * sizeof(unsigned long long), c->stream));
+        c->hs_words = nw + zw + sw; c->hs_P = c->P;
     }
-    out->nodes = c->d_hs; out->zt = c->d_hs + nw; out->epoch = c->hs_epoch;
+    out->nodes = c->d_hs; out->zt = c->d_hs + nw; out->epoch = c->hs_epoch; out->state = c->d_hs + nw + zw;
     return PMP_OK;
 }
 
@@ -784,6 +784,8 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     pa.max_chunks = (int)max_chunks;
     const bool hs = env_int("PMP_HANDOFF", 1) != 0;   // flag-in-data hand-offs (default) or release/acquire counters
     if (hs && (rc = ensure_handoff(c, &pa.hs))) return rc;
+    // flat tree: a node is state + alpha * z(node) — the acceptance publishes the accepted state and every reader derives its nodes (Handoff::state)
+    pa.derive = hs && c->cfg.tree == PMP_TREE_FLAT && c->cfg.dim == 3 && n_sweep >= ntiles && env_int("PMP_DERIVE_NODES", 1);
     void* kargs[] = {&pa};
     const void* fn;
 #define PMP_SINGLE_FN(ALGO) (hs ? (const void*)chain_persistent_kernel<ALGO, true> : (const void*)chain_persistent_kernel<ALGO, false>)
@@ -798,7 +800,7 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     PMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PERSIST_THREADS, smem));
     if (per_sm < 1) return 0;
     PMP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PERSIST_THREADS), kargs, smem, c->stream));
-    if (hs) c->hs_epoch += (unsigned int)iters;
+    if (hs) c->hs_epoch += (unsigned int)iters + (pa.derive ? 1u : 0u);     // derive: the tag after the last iteration's is used too (state and normals of the iteration after the launch)
     c->launches++;
     c->host_iter += (unsigned long long)iters;
     c->z_valid_iter = -1;
@@ -1050,6 +1052,7 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
         PMP_CUDA(cudaStreamSynchronize(c->stream));                // everything queued on this chain's own stream is done before the joint launch
     }
     pa.n_chains = K; pa.iters = (int)iters; pa.max_chunks = (int)max_chunks; pa.n_accept = n_accept;
+    pa.derive = hs && K == 1 && c0->cfg.tree == PMP_TREE_FLAT && c0->cfg.dim == 3 && (G - n_accept) >= (c0->P + PERSIST_PT - 1) / PERSIST_PT && env_int("PMP_DERIVE_NODES", 1);
     void* kargs[] = {&pa};
     const void* fn;
     const int groups_dflt = K >= 8 ? 8 : (K >= 4 ? 4 : 2);                             // warp groups per sweep CTA (measured, scripts/tune_multi.py)
@@ -1077,7 +1080,7 @@ static int run_multi_impl(pmp_ctx** cs, int K, int64_t iters, cudaEvent_t ev_beg
         pmp_ctx* c = cs[k];
         if (k > 0) PMP_CUDA(cudaStreamWaitEvent(c->stream, c0->ev1, 0));   // later work on the chain's own stream is ordered after the joint kernel
         if (c->world > 1) c->xchg_count += (unsigned long long)iters;       // only once the launch is in the stream: a failed launch must not shift the tags
-        if (hs) c->hs_epoch += (unsigned int)iters;
+        if (hs) c->hs_epoch += (unsigned int)iters + (pa.derive ? 1u : 0u);
         c->host_iter += (unsigned long long)iters;
         c->z_valid_iter = -1;
         c->lt_valid = false;
