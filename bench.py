@@ -595,7 +595,7 @@ def main():
                            "P": P_NODES, "n": n_global, "chains": 1, "iters_per_step": iters, "device": info["name"],
                            "l2": "flushed (256 MB memset) between steps; inside a step the dataset is re-read from L2 by design",
                            "baseline": "reference README.md:44: (33473.53 + 1099.258) us per iteration at P=1024, n=100000, one chain; README says A100, the shipped .nvvp files say V100-SXM2",
-                           "scaling_note": "`value` is ONE chain: a strict dependency loop of ~9 us of sweep and ~8 us of hand-off / acceptance latency per iteration at N=1; sharding the rows shrinks only the "
+                           "scaling_note": "`value` is ONE chain: a strict dependency loop of ~11 us of sweep and ~4.5 us of hand-off / acceptance latency per iteration at N=1; sharding the rows shrinks only the "
                                            "sweep (SURVEY 8e expects this configuration to be exchange-latency bound: flat or negative scaling).  The sharded WORKLOAD that scales is in the extra blocks of this "
                                            "line: `co_scheduled` (independent chains in one cooperative kernel per GPU, in-kernel NVLink exchange), `fc` and `cnn` (rows sharded, integer loss sums all-reduced)"},
                 "clocks": clocks,

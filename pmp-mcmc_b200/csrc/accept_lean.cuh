@@ -144,8 +144,13 @@ __device__ __forceinline__ void lean_pre(const AcceptFastArgs& fa, const LeanSme
     const int P = a.P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long* dbg = a.dbg ? a.dbg + 32 : nullptr;
     PMP_STAMP(dbg, 0);
-    r.iter = __ldcg(&a.cnt->iteration);
-    r.row = __ldcg(&a.cnt->trace_rows);
+    if (z_mode == LEAN_Z_DERIVE && !first) {      // the counters this CTA advanced itself in the previous iteration (crit / post): no L2 round trip, and no fence needed after post
+        r.iter += 1;
+        if (r.row < a.trace.capacity) r.row += 1;
+    } else {
+        r.iter = __ldcg(&a.cnt->iteration);
+        r.row = __ldcg(&a.cnt->trace_rows);
+    }
     const int n_draws = (cfg.draw == PMP_DRAW_SINGLE) ? 1 : P;
     if (tid == 0) {
         double up = 0.0;

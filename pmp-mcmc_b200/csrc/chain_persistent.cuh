@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
             }
             if (pa.fa.base.dbg && tid == 0) { pa.fa.base.dbg[32 + 9] = clock64(); pa.fa.base.dbg[32 + 25] = globaltimer_ns(); }
             lean_post<ALGO>(pa.fa, ls, lr);
-            __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre / by the host
+            if (!(HS && pa.derive)) __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre (derive: nothing is; the host reads after the kernel)
             __syncthreads();
         }
         if (HS && pa.derive && pa.iters > 0) {      // the nodes of the iteration after the last one: the plain copy the host and the next launch read

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_multi_ker
                     if (tid == 0) st_release(&pa.ch[c].sync->version, (unsigned)(it + 1));
                 }
                 lean_post<ALGO>(fa, ls, lr);
-                __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre of this chain / by the host
+                if (!(HS && pa.derive)) __threadfence();          // trace cursor, state and the plain copy of the nodes are read back by the next pre of this chain (derive: nothing is)
                 __syncthreads();
             }
         }
