@@ -22,16 +22,18 @@ struct ChainArgs {
     float* states;            // [dim][n_chains]
     float* nodes;             // [P][dim][n_chains] scratch
     double* work;             // [3][P][n_chains] scratch: lt, A/cdf, level scratch
-    int* draws;               // [P][n_chains] scratch
+    unsigned short* draws;    // [P][n_chains] scratch (P <= MAX_NODES = 8192)
+    int tmp_slots;            // level scratch entries per chain: b for the general-tree rule, else 0
     float* samples;           // [iters][P][dim][n_chains] or nullptr
     unsigned long long seed, iter0;
     int iters;
 };
 
-// Scratch of a chain (tree nodes, log-targets, weights / cdf, level scratch, draws): P * (4 dim + 28) bytes.  SM = true keeps it in SHARED
+// Scratch of a chain (log-targets, weights / cdf: binary64; level scratch of the general-tree rule: b binary64; tree nodes: float32; draws: 16-bit): P * (4 dim + 18) + 8 b
+// bytes — 448 for the banana PMP (P = 16, b = 4, dim = 2).  SM = true keeps it in SHARED
 // memory ([slot][thread]: conflict-free) — round 1 kept it in global memory, and with 2^20 chains it spilled out of L2: 11.8 GB of DRAM
 // writes per launch against 3.2 GB of recorded samples (ncu r1c).  SM = false is the fallback for trees too large for shared memory.
-__host__ __device__ inline size_t chain_scratch_bytes(int P, int dim) { return (size_t)P * (4 * (size_t)dim + 28); }
+__host__ __device__ inline size_t chain_scratch_bytes(int P, int dim, int tmp_slots) { return (size_t)P * (4 * (size_t)dim + 18) + 8 * (size_t)tmp_slots; }
 
 __device__ __forceinline__ double chain_log_kernel(const float* nodes, long long nc, int dim, int a, int b, long long c, double ks, double lnk) {
     double s = 0.0;
@@ -56,8 +58,9 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
     // scratch addressing: element e of an array lives at [e * sn + so]
     const long long sn = SM ? (long long)blockDim.x : nc, so = SM ? (long long)threadIdx.x : c;
     double* const work = SM ? reinterpret_cast<double*>(chain_sm) : a.work;
-    float* const nodes = SM ? reinterpret_cast<float*>(chain_sm + (size_t)3 * P * blockDim.x * sizeof(double)) : a.nodes;
-    int* const draws = SM ? reinterpret_cast<int*>(chain_sm + (size_t)3 * P * blockDim.x * sizeof(double) + (size_t)P * dim * blockDim.x * sizeof(float)) : a.draws;
+    const size_t nd = (size_t)2 * P + a.tmp_slots;        // binary64 slots per chain
+    float* const nodes = SM ? reinterpret_cast<float*>(chain_sm + nd * blockDim.x * sizeof(double)) : a.nodes;
+    unsigned short* const draws = SM ? reinterpret_cast<unsigned short*>(chain_sm + nd * blockDim.x * sizeof(double) + (size_t)P * dim * blockDim.x * sizeof(float)) : a.draws;
     const int b = (cfg.tree == PMP_TREE_BINARY) ? 2 : cfg.b;
     const int D = (cfg.tree == PMP_TREE_FLAT) ? 1 : cfg.depth;
     const double ks = (double)cfg.kernel_sigma;
@@ -83,12 +86,19 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
         // half of the kernel's instructions).  Phase 2 adds the parents in index order: child = fl(parent + fl(alpha z)), the same bits.
         if (live) for (int j = 0; j < dim; ++j) NODE(0, j) = a.states[(long long)j * nc + c];
         if (!COMPACT) {
-            for (int p = 1; p < P; ++p) {
-                int parent = 0;
-                if (cfg.tree != PMP_TREE_FLAT) { long long s = 1; while ((long long)p >= s * b) s *= b; parent = (int)(p % s); }
-                for (int j = 0; j < dim; ++j) {
-                    float z = (float)stream_step(a.seed, iter, cbase | (unsigned long long)((long long)p * dim + j), uniform);
-                    NODE(p, j) = __fadd_rn(NODE(parent, j), __fmul_rn(cfg.alpha, z));
+            // short trees: per-element quantiles (both branches inline), but still one Philox block per element PAIR
+            const int e_hi = P * dim;
+            for (int k = dim >> 1; 2 * k < e_hi; ++k) {
+                const unsigned long long blk = (cbase | (unsigned long long)(2 * k)) >> 1;
+                uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)iter, ((uint32_t)(iter >> 32) & 0x00FFFFFFu) | (STREAM_PROPOSAL << 24)};
+                philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                const uint64_t w[2] = {(uint64_t)ctr[1] << 32 | ctr[0], (uint64_t)ctr[3] << 32 | ctr[2]};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = 2 * k + h;
+                    if (e < dim || e >= e_hi) continue;
+                    const double step = uniform ? PMP_FMA(2.0, u64_to_unit(w[h]), -1.0) : det_norm_ppf(u64_to_open(w[h]));
+                    nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)step);
                 }
             }
         } else {
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             __syncwarp();
         }
         if (live) {
-        if (COMPACT) for (int p = 1; p < P; ++p) {
+        for (int p = 1; p < P; ++p) {
             int parent = 0;
             if (cfg.tree != PMP_TREE_FLAT) { long long s = 1; while ((long long)p >= s * b) s *= b; parent = (int)(p % s); }
             for (int j = 0; j < dim; ++j) NODE(p, j) = __fadd_rn(NODE(parent, j), NODE(p, j));
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             double l0 = W(lt, 0), l1 = W(lt, 1);
             if (cfg.algo == PMP_ALGO_MH) next = u < exp((double)cfg.mh_temperature * (l1 - l0));
             else { double m = fmax(l0, l1); double w0 = exp(l0 - m), w1 = exp(l1 - m); next = (w1 / (w0 + w1)) > u; }
-            W(draws, 0) = next; n_draws = 1;
+            W(draws, 0) = (unsigned short)next; n_draws = 1;
             W(A, 0) = l0; W(A, 1) = l1;
         } else {
             if (cfg.algo == PMP_ALGO_MP) {
@@ -174,12 +184,12 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                             int nj = (int)(h + j * s);
                             double v = W(lt, nj);
                             if (use_kernel) for (int k = 0; k < b; ++k) if (k != j) v += chain_log_kernel(nodes, sn, dim, nj, (int)(h + k * s), so, ks, lnk);
-                            W(tmp, nj) = v; mx = fmax(mx, v);
+                            W(tmp, j) = v; mx = fmax(mx, v);
                         }
                         double se = 0.0;
-                        for (int j = 0; j < b; ++j) se += exp(W(tmp, h + j * s) - mx);
+                        for (int j = 0; j < b; ++j) se += exp(W(tmp, j) - mx);
                         double lse = mx + log(se);
-                        for (int j = 0; j < b; ++j) { int nj = (int)(h + j * s); W(A, nj) += (mx == -INFINITY) ? -INFINITY : W(tmp, nj) - lse; }
+                        for (int j = 0; j < b; ++j) { int nj = (int)(h + j * s); W(A, nj) += (mx == -INFINITY) ? -INFINITY : W(tmp, j) - lse; }
                     }
                     if (i < D - 1) {
                         long long lo = s * b, hi = s * b * b;
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                 double thr = u64_to_unit(word) * total;
                 int lo = 0, hi = P;
                 while (lo < hi) { int mid = (lo + hi) >> 1; double v = W(A, mid); bool go = right ? (v <= thr) : (v < thr); if (go) lo = mid + 1; else hi = mid; }
-                W(draws, t) = min(lo, P - 1);
+                W(draws, t) = (unsigned short)min(lo, P - 1);
             }
             if (cfg.draw == PMP_DRAW_PYTHON) {
                 double up = u64_to_unit(stream_u64(a.seed, iter, STREAM_PICK, cbase));
@@ -327,22 +337,24 @@ static int chains_launch(pmp_ctx* c, int64_t iters, int record) {
             c->chain_samples_cap = need;
         }
     }
-    ChainArgs a{c->cfg, c->P, c->n_chains, c->d_chain_states, s->nodes, s->work, s->draws, record ? c->d_chain_samples : nullptr,
+    const int tmp_slots = c->cfg.algo == PMP_ALGO_PMP ? (c->cfg.tree == PMP_TREE_BINARY ? 2 : c->cfg.b) : 0;
+    ChainArgs a{c->cfg, c->P, c->n_chains, c->d_chain_states, s->nodes, s->work, reinterpret_cast<unsigned short*>(s->draws), tmp_slots, record ? c->d_chain_samples : nullptr,
                 c->seed, c->chain_iteration, (int)iters};
-    // scratch in shared memory when a block of >= 32 chains fits ~96 KB (two blocks per SM), else in global memory
-    const size_t per_chain = chain_scratch_bytes(c->P, c->cfg.dim);
-    int threads = 128;
-    while (threads > 32 && per_chain * threads > 96 * 1024) threads >>= 1;
-    const bool in_smem = per_chain * threads <= 96 * 1024 && !getenv("PMP_CHAINS_GLOBAL_SCRATCH");
+    // scratch in shared memory when a block of >= 32 chains fits 100 KB (the largest such block), else in global memory
+    const size_t per_chain = chain_scratch_bytes(c->P, c->cfg.dim, tmp_slots);
     const bool compact = !(c->cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) && (long long)(c->P - 1) * c->cfg.dim >= 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    int threads = 0;
+    for (int t = 128; t >= 32 && !threads; t >>= 1) if (per_chain * t <= 100 * 1024) threads = t;      // measured (banana PMP): 128-thread blocks 25.9 ms, 64 28.6, 32 27.9 — more resident warps from smaller blocks do not pay
+    if (getenv("PMP_CHAINS_THREADS")) { const int t = atoi(getenv("PMP_CHAINS_THREADS")); if ((t == 32 || t == 64 || t == 128) && per_chain * t <= 100 * 1024) threads = t; }
+    const bool in_smem = threads > 0 && !getenv("PMP_CHAINS_GLOBAL_SCRATCH");
     if (in_smem) {
         const size_t smem = per_chain * threads;
-        static size_t attr_set = 0;
-        if (smem > attr_set) {
-            PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            PMP_CUDA(cudaFuncSetAttribute(chains_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = 100 * 1024;
-        }
         const unsigned grid = (unsigned)((c->n_chains + threads - 1) / threads);
         if (compact) chains_kernel<true, true><<<grid, threads, smem, c->stream>>>(a);
         else chains_kernel<true, false><<<grid, threads, smem, c->stream>>>(a);
