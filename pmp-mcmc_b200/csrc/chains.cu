@@ -35,13 +35,15 @@ struct ChainArgs {
 // writes per launch against 3.2 GB of recorded samples (ncu r1c).  SM = false is the fallback for trees too large for shared memory.
 __host__ __device__ inline size_t chain_scratch_bytes(int P, int dim, int tmp_slots) { return (size_t)P * (4 * (size_t)dim + 18) + 8 * (size_t)tmp_slots; }
 
-__device__ __forceinline__ double chain_log_kernel(const float* nodes, long long nc, int dim, int a, int b, long long c, double ks, double lnk) {
+// log K(a, b) of the Gaussian proposal kernel.  Symmetric to the last bit (the differences only change sign), which the callers use to evaluate every pair once.
+// ks2 = ks * ks; a division by exactly 1.0 returns its dividend, so the default kernel_sigma = 1 skips the binary64 division.
+__device__ __forceinline__ double chain_log_kernel(const float* nodes, long long nc, int dim, int a, int b, long long c, double ks2, double lnk) {
     double s = 0.0;
     for (int j = 0; j < dim; ++j) {
         double d = (double)nodes[((long long)a * dim + j) * nc + c] - (double)nodes[((long long)b * dim + j) * nc + c];
         s = fma(d, d, s);
     }
-    return dim * lnk - 0.5 * s / (ks * ks);
+    return ks2 == 1.0 ? dim * lnk - 0.5 * s : dim * lnk - 0.5 * s / ks2;
 }
 
 // COMPACT: the warp-cooperative increments phase for long trees ((P - 1) * dim >= 64 normals per hop); short trees keep the per-element loop — with the 30 increments of the
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
     unsigned short* const draws = SM ? reinterpret_cast<unsigned short*>(chain_sm + nd * blockDim.x * sizeof(double) + (size_t)P * dim * blockDim.x * sizeof(float)) : a.draws;
     const int b = (cfg.tree == PMP_TREE_BINARY) ? 2 : cfg.b;
     const int D = (cfg.tree == PMP_TREE_FLAT) ? 1 : cfg.depth;
-    const double ks = (double)cfg.kernel_sigma;
+    const double ks = (double)cfg.kernel_sigma, ks2 = ks * ks;
     const double lnk = -HALF_LOG_2PI - log(ks);
     const bool use_kernel = !(cfg.flags & PMP_FLAG_NO_KERNEL_TERM);
     const int uniform = (cfg.flags & PMP_FLAG_UNIFORM_PROPOSAL) ? 1 : 0;
@@ -144,10 +146,16 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             __syncwarp();
         }
         if (live) {
-        for (int p = 1; p < P; ++p) {
-            int parent = 0;
-            if (cfg.tree != PMP_TREE_FLAT) { long long s = 1; while ((long long)p >= s * b) s *= b; parent = (int)(p % s); }
-            for (int j = 0; j < dim; ++j) NODE(p, j) = __fadd_rn(NODE(parent, j), NODE(p, j));
+        if (cfg.tree == PMP_TREE_FLAT) {
+            for (int p = 1; p < P; ++p) for (int j = 0; j < dim; ++j) NODE(p, j) = __fadd_rn(NODE(0, j), NODE(p, j));
+        } else {
+            for (int s = 1; s < P; s *= b) {                 // level: nodes [s, s b), node p hangs under p mod s
+                int parent = 0;
+                for (int p = s; p < s * b && p < P; ++p) {
+                    for (int j = 0; j < dim; ++j) NODE(p, j) = __fadd_rn(NODE(parent, j), NODE(p, j));
+                    if (++parent == s) parent = 0;
+                }
+            }
         }
         // ---- log-targets
         for (int p = 0; p < P; ++p) W(lt, p) = analytic_logtarget(cfg.target, &NODE(p, 0), (int)sn, dim, cfg.target_p0, cfg.target_p1) / (double)cfg.scale;
@@ -163,10 +171,11 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
             W(A, 0) = l0; W(A, 1) = l1;
         } else {
             if (cfg.algo == PMP_ALGO_MP) {
-                for (int j = 0; j < P; ++j) {
-                    double v = W(lt, j);
-                    if (use_kernel) for (int k = 0; k < P; ++k) if (k != j) v += chain_log_kernel(nodes, sn, dim, j, k, so, ks, lnk);
-                    W(A, j) = v;
+                // A[j] = lt[j] + sum_{k != j, ascending} log K(j, k): every pair is evaluated once and added to both ends — node j still receives its terms in ascending k
+                for (int j = 0; j < P; ++j) W(A, j) = W(lt, j);
+                if (use_kernel) for (int j = 0; j < P; ++j) for (int k = j + 1; k < P; ++k) {
+                    const double kv = chain_log_kernel(nodes, sn, dim, j, k, so, ks2, lnk);
+                    W(A, j) += kv; W(A, k) += kv;
                 }
             } else if (cfg.algo == PMP_ALGO_PSP) {
                 for (int p = 0; p < P; ++p) {
@@ -176,25 +185,26 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                 }
             } else if (cfg.algo == PMP_ALGO_PMP) {
                 for (int p = 0; p < P; ++p) W(A, p) = 0.0;
-                long long s = 1;
+                int s = 1;
                 for (int i = 0; i < D; ++i) {
-                    for (long long h = 0; h < s; ++h) {
-                        double mx = -INFINITY;
-                        for (int j = 0; j < b; ++j) {
-                            int nj = (int)(h + j * s);
-                            double v = W(lt, nj);
-                            if (use_kernel) for (int k = 0; k < b; ++k) if (k != j) v += chain_log_kernel(nodes, sn, dim, nj, (int)(h + k * s), so, ks, lnk);
-                            W(tmp, j) = v; mx = fmax(mx, v);
+                    for (int h = 0; h < s; ++h) {
+                        for (int j = 0; j < b; ++j) W(tmp, j) = W(lt, h + j * s);
+                        if (use_kernel) for (int j = 0; j < b; ++j) for (int k = j + 1; k < b; ++k) {      // every pair once, same order of additions per node (see MP)
+                            const double kv = chain_log_kernel(nodes, sn, dim, h + j * s, h + k * s, so, ks2, lnk);
+                            W(tmp, j) += kv; W(tmp, k) += kv;
                         }
+                        double mx = -INFINITY;
+                        for (int j = 0; j < b; ++j) mx = fmax(mx, W(tmp, j));
                         double se = 0.0;
                         for (int j = 0; j < b; ++j) se += exp(W(tmp, j) - mx);
                         double lse = mx + log(se);
-                        for (int j = 0; j < b; ++j) { int nj = (int)(h + j * s); W(A, nj) += (mx == -INFINITY) ? -INFINITY : W(tmp, j) - lse; }
+                        for (int j = 0; j < b; ++j) { const int nj = h + j * s; W(A, nj) += (mx == -INFINITY) ? -INFINITY : W(tmp, j) - lse; }
                     }
                     if (i < D - 1) {
-                        long long lo = s * b, hi = s * b * b;
-                        long long mod = (cfg.flags & PMP_FLAG_QUIRK_LEVEL_MOD) ? (long long)b * (i + 1) : lo;
-                        for (long long x = lo; x < hi; ++x) W(A, x) = W(A, x % mod);
+                        const int lo = s * b, hi = s * b * b;
+                        const int mod = (cfg.flags & PMP_FLAG_QUIRK_LEVEL_MOD) ? b * (i + 1) : lo;
+                        int r = lo % mod;
+                        for (int x = lo; x < hi; ++x) { W(A, x) = W(A, r); if (++r == mod) r = 0; }
                     }
                     s *= b;
                 }
@@ -203,10 +213,10 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                     double v = W(lt, p);
                     if (cfg.flags & PMP_FLAG_QUIRK_TABLE_CONST) v += (double)D * (b - 1) * dim * (-HALF_LOG_2PI);
                     else if (use_kernel) {
-                        long long s = 1;
+                        int s = 1;
                         for (int d = 0; d < D; ++d) {
-                            long long m = p % (s * b), h = m % s;
-                            for (int k = 0; k < b; ++k) { long long o = h + k * s; if (o != m) v += chain_log_kernel(nodes, sn, dim, (int)m, (int)o, so, ks, lnk); }
+                            const int m = p % (s * b), h = m % s;
+                            for (int k = 0; k < b; ++k) { const int o = h + k * s; if (o != m) v += chain_log_kernel(nodes, sn, dim, m, o, so, ks2, lnk); }
                             s *= b;
                         }
                     }
