@@ -88,8 +88,12 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
         // half of the kernel's instructions).  Phase 2 adds the parents in index order: child = fl(parent + fl(alpha z)), the same bits.
         if (live) for (int j = 0; j < dim; ++j) NODE(0, j) = a.states[(long long)j * nc + c];
         if (!COMPACT) {
-            // short trees: per-element quantiles (both branches inline), but still one Philox block per element PAIR
+            // short trees: one Philox block per element PAIR; the quantile's central branch inline, its tail branch (15 % of the draws) deferred: with 30 increments
+            // nearly every warp holds a tail lane for every element, so evaluating in place makes the warp run both branches 30 times.  A lane parks its tail draws
+            // (element in the draws slots, uniform in the binary64 slots — both unused until the weights) and the warp then runs the tail code max-over-lanes times.
             const int e_hi = P * dim;
+            int n_tail = 0;
+            const int cap = (e_hi - dim >= 16) ? P : 0;      // parked entries: draws has P slots, the binary64 scratch 2 P.  Measured: 30 increments (banana PMP) 22.4 -> 21.6 ms, 3 increments (1-D MP) 23.7 -> 24.9: in place below 16
             for (int k = dim >> 1; 2 * k < e_hi; ++k) {
                 const unsigned long long blk = (cbase | (unsigned long long)(2 * k)) >> 1;
                 uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)iter, ((uint32_t)(iter >> 32) & 0x00FFFFFFu) | (STREAM_PROPOSAL << 24)};
@@ -99,9 +103,17 @@ __global__ void __launch_bounds__(128) chains_kernel(ChainArgs a) {
                 for (int h = 0; h < 2; ++h) {
                     const int e = 2 * k + h;
                     if (e < dim || e >= e_hi) continue;
-                    const double step = uniform ? PMP_FMA(2.0, u64_to_unit(w[h]), -1.0) : det_norm_ppf(u64_to_open(w[h]));
-                    nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)step);
+                    if (uniform) { nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)PMP_FMA(2.0, u64_to_unit(w[h]), -1.0)); continue; }
+                    const double u = u64_to_open(w[h]);
+                    const double q = PMP_ADD(u, -0.5);
+                    if (fabs(q) <= 0.425) nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)ppf_central(q));
+                    else if (n_tail < cap) { W(draws, n_tail) = (unsigned short)e; W(work, n_tail) = u; ++n_tail; }
+                    else nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)det_norm_ppf(u));
                 }
+            }
+            for (int i = 0; i < n_tail; ++i) {
+                const int e = W(draws, i);
+                nodes[(long long)e * sn + so] = __fmul_rn(cfg.alpha, (float)det_norm_ppf(W(work, i)));
             }
         } else {
             int qn = 0;
