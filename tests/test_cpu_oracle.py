@@ -152,6 +152,35 @@ def test_no_gpu_means_loud_failure():
         pm.Context(0)
 
 
+def test_null_arguments_are_errors_not_crashes():
+    """Argument validation comes before any CUDA call: NULL contexts / pointers return a negative status and a message, with or without a GPU."""
+    import ctypes
+    from pmp_mcmc_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.Config(_lib.TREE_FLAT, 4, 1, 3, _lib.TARGET_LINEAR_GAUSS, _lib.ALGO_MP, _lib.DRAW_PYTHON, 0, 0.01, 1.0, 1.0, 0.0, 1.0, 1.0)
+    calls = [lambda: lib.pmp_create(None, 0, 1, 0, None),
+             lambda: lib.pmp_create(ctypes.byref(ctypes.c_void_p()), 0, 0, 0, None),
+             lambda: lib.pmp_create(ctypes.byref(ctypes.c_void_p()), 0, 2, 5, None),
+             lambda: lib.pmp_configure(None, ctypes.byref(cfg)),
+             lambda: lib.pmp_set_data_linear(None, None, None, 0, 0, 0),
+             lambda: lib.pmp_set_state(None, None, 3),
+             lambda: lib.pmp_seed(None, 1, 0),
+             lambda: lib.pmp_propose(None),
+             lambda: lib.pmp_loglik(None, None),
+             lambda: lib.pmp_accept(None, None, 0, None, None),
+             lambda: lib.pmp_run(None, 10, 1),
+             lambda: lib.pmp_run_multi(None, 1, 10, 1),
+             lambda: lib.pmp_trace_config(None, 10, 1),
+             lambda: lib.pmp_read_trace(None, 10, None, None, None, None, None, None),
+             lambda: lib.pmp_hmc_accept(None, 0, 2, None, None, None, 0.5, 1.0, None, None),
+             lambda: lib.pmp_nccl_unique_id(None)]
+    for i, call in enumerate(calls):
+        rc = call()
+        assert rc < 0, (i, rc)
+        assert len(lib.pmp_last_error()) > 0, i
+    assert lib.pmp_destroy(None) in (0, -1, -2, -3, -4, -5)          # destroying nothing is not a crash either
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "pmp-mcmc_b200")
     for dirpath, _, files in os.walk(pkg):

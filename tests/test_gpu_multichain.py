@@ -143,3 +143,35 @@ def test_headline_shape_co_scheduled_equals_solo():
         s.close()
     for c in reversed(ctxs):
         c.close()
+
+
+@pytest.mark.parametrize("P,n", [(1024, 20000), (37, 5000), (4, 500), (2048, 3000), (130, 64)])
+def test_state_only_handoff_equals_node_handoff(P, n, monkeypatch):
+    """Flat trees in the persistent kernels: the acceptance publishes the accepted state and every reader derives its nodes (Handoff::state, DESIGN 4.0) —
+    the traces, the draws, the log-weights and the nodes left behind must equal those of the hand-off that publishes every node (PMP_DERIVE_NODES=0),
+    across launch boundaries and for a co-scheduled launch of one chain (chain_persistent_multi_kernel takes the same path for K = 1)."""
+    import pmp_mcmc_b200 as pm
+    from pmp_mcmc_b200 import _lib as L
+    x, y = synthetic_linear(n, seed=5)
+    what = L.TRACE_STATE | L.TRACE_NEXT | L.TRACE_DRAWS | L.TRACE_LOGW
+    res = {}
+    for mode in ("0", "1", "multi"):
+        monkeypatch.setenv("PMP_DERIVE_NODES", "0" if mode == "0" else "1")
+        c = pm.Context(0)
+        c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_PYTHON, alpha=0.02, scale=max(n / 100.0, 1.0))
+        c.set_data_linear(x, y); c.set_state([0.5, 1.0, 1.5]); c.seed(11, 0)
+        c.trace_config(200, what)
+        if mode == "multi":
+            for iters in (3, 60, 2, 35):
+                L.run_multi([c], iters)
+        else:
+            for iters in (3, 60, 2, 35):          # 2 iterations: the shortest launch the persistent kernel takes
+                c.run(iters)
+        tr = c.read_trace()
+        res[mode] = (tr, c.read_proposals().copy(), c.get_state().copy())
+        c.close()
+    for mode in ("1", "multi"):
+        for key in ("state", "next", "draws", "logw"):
+            assert np.array_equal(res["0"][0][key], res[mode][0][key]), (mode, key)
+        assert np.array_equal(res["0"][1], res[mode][1]), mode
+        assert np.array_equal(res["0"][2], res[mode][2]), mode
