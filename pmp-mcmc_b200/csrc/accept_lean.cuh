@@ -123,15 +123,15 @@ __device__ __forceinline__ void lean_read_tagged_z(const LeanSmem& s, const unsi
 }
 
 // DERIVE: the nodes of iteration `iter` from the state the previous critical phase accepted (r.n0..n2) and the tagged normals of `iter`, into shared memory and
-// into the plain copy in global memory (host reads, first iteration of the next launch).  Same expression as proposal_value_zs for a flat tree.
+// into the plain copy in global memory (host reads, first iteration of the next launch).
 __device__ __forceinline__ void lean_derive_props(const AcceptFastArgs& fa, const LeanSmem& s, const LeanRegs& r, const Handoff& hs, unsigned long long iter, unsigned long long tag) {
     const int P = fa.base.P, tid = threadIdx.x;
     lean_read_tagged_z(s, hs.zt + (iter & 1) * (long long)(P * 3), P, tag);
     float* props_out = const_cast<float*>(fa.base.props);
-    for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) {      // thread g reads the s.z[g] it wrote itself
+    if (fa.gen.tree != PMP_TREE_FLAT) __syncthreads();      // a tree node reads its ancestors' normals, written by other threads (flat: thread g reads the s.z[g] it wrote itself)
+    for (int g = tid; g < 3 * P; g += ACCEPT_THREADS) {
         const int node = g / 3, j = g - 3 * node;
-        float v = j == 0 ? r.n0 : (j == 1 ? r.n1 : r.n2);
-        if (node > 0) v = __fadd_rn(v, __fmul_rn(fa.gen.alpha, s.z[g]));
+        const float v = proposal_value_zs(fa.gen, s.z, node, j, j == 0 ? r.n0 : (j == 1 ? r.n1 : r.n2));
         s.props[g] = v; props_out[g] = v;
     }
 }

@@ -34,7 +34,7 @@ struct PersistArgs {
     int iters;
     int max_chunks;          // chunks per sweep CTA that fit the dynamic shared memory
     Handoff hs;              // HS kernels: flag-in-data hand-offs (accept_lean.cuh)
-    int derive;              // HS, flat tree, one segment per sweep CTA: the acceptance publishes the accepted state only and every reader derives its nodes (Handoff::state)
+    int derive;              // HS, flat or binary tree, one segment per sweep CTA: the acceptance publishes the accepted state only and every reader derives its nodes (Handoff::state)
 };
 
 // A sweep CTA's thread i < PERSIST_PT fetches node (node_base + i) of iteration `it`: plain memory for the first iteration of a launch
@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
     unsigned long long* sred = reinterpret_cast<unsigned long long*>(tile + (size_t)pa.max_chunks * CHUNK_STRIDE);   // [TD][PT]
     __shared__ float sprops[PT * 3];
     __shared__ double sscl[PT];
-    __shared__ float saz[PT * 3];            // derive: alpha * z of this CTA's tile for the coming iteration
+    // derive: alpha * z of the coming iteration for the tiles this CTA's nodes depend on.  Flat tree: its own tile.  Binary tree: node 128 t + i is the state plus the
+    // increments of its ancestors in creation order — the low-bit prefixes of i (all in tile 0), then element i of the tiles whose index is a low-bit prefix of t, t
+    // itself last (for_each_ancestor) — so the list is {0, prefixes of t .. t}: at most 1 + popcount(t) <= 5 tiles for P <= 2048.
+    constexpr int DERIVE_TILES = 5;
+    __shared__ float saz[DERIVE_TILES * PT * 3];
     __shared__ float s_state[4];
 
     const int tp = tid & (TP - 1), td = tid / TP;
@@ -223,7 +227,21 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
                         const int node = node_base + tid;
                         v0 = s_state[0]; v1 = s_state[1]; v2 = s_state[2];
                         if (node >= a.P) { v0 = 0.f; v1 = 0.f; v2 = 0.f; }
-                        else if (node > 0) { v0 = __fadd_rn(v0, saz[3 * tid]); v1 = __fadd_rn(v1, saz[3 * tid + 1]); v2 = __fadd_rn(v2, saz[3 * tid + 2]); }
+                        else if (a.gen.tree == PMP_TREE_FLAT) {
+                            if (node > 0) { v0 = __fadd_rn(v0, saz[3 * tid]); v1 = __fadd_rn(v1, saz[3 * tid + 1]); v2 = __fadd_rn(v2, saz[3 * tid + 2]); }
+                        } else {
+                            const int t = seg_tile[s];
+                            for (int l = 0; l < 7; ++l) if ((tid >> l) & 1) {                 // ancestors inside tile 0: the low-bit prefixes of i
+                                const float* z3 = saz + 3 * (tid & ((2 << l) - 1));
+                                v0 = __fadd_rn(v0, z3[0]); v1 = __fadd_rn(v1, z3[1]); v2 = __fadd_rn(v2, z3[2]);
+                            }
+                            int k = 1;
+                            for (int l = 0; l < 4; ++l) if ((t >> l) & 1) {                   // element i of the prefix tiles of t, t itself last
+                                const float* z3 = saz + (k * PT + tid) * 3;
+                                v0 = __fadd_rn(v0, z3[0]); v1 = __fadd_rn(v1, z3[1]); v2 = __fadd_rn(v2, z3[2]);
+                                ++k;
+                            }
+                        }
                     } else
                     fetch_node(pa.hs, a.theta, node_base + tid, a.P, it == 0, tag, v0, v1, v2);
                     sprops[3 * tid] = v0; sprops[3 * tid + 1] = v1; sprops[3 * tid + 2] = v2;
@@ -272,17 +290,20 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) chain_persistent_kernel(co
         if (tid == 0) atomicAdd(&pa.sync->arrive, 1u);
         PMP_STAMP(dbg, 5);
         if (HS && pa.derive && nseg == 1) {
-            // while the acceptance runs: the normals of the NEXT iteration's nodes of this tile (every CTA of a tile computes them for itself; the
-            // tile's first CTA also hands them to the acceptance CTA, which needs all nodes for its own pre phase — off the critical path)
+            // while the acceptance runs: the normals of the NEXT iteration's nodes of this tile (and, binary tree, of the tiles they descend from).  Every CTA computes
+            // them for itself; the tile's first CTA also hands its own tile's to the acceptance CTA, which needs all nodes for its own pre phase — off the critical path
             const unsigned long long iter = iter0 + (unsigned long long)it + 1;
             const bool publish = seg_c0[0] == 0;
-            const int zcount = a.P * 3;
-            for (int i = tid; i < PT * 3; i += PERSIST_THREADS) {
-                const int e = seg_tile[0] * PT * 3 + i;
+            const int zcount = a.P * 3, t = seg_tile[0];
+            int tiles[DERIVE_TILES], nt = 0;
+            if (a.gen.tree == PMP_TREE_FLAT) tiles[nt++] = t;
+            else { tiles[nt++] = 0; for (int l = 0; l < 4; ++l) if ((t >> l) & 1) tiles[nt++] = t & ((2 << l) - 1); }
+            for (int i = tid; i < nt * PT * 3; i += PERSIST_THREADS) {
+                const int k = i / (PT * 3), u = tiles[k], e = u * PT * 3 + (i - k * PT * 3);
                 if (e < zcount) {
                     const float zv = (float)stream_step(a.gen.seed, iter, (unsigned long long)e, a.gen.uniform);
                     saz[i] = __fmul_rn(a.gen.alpha, zv);
-                    if (publish) st_relaxed_gpu_u64(pa.hs.zt + (iter & 1) * (long long)zcount + e, (unsigned long long)__float_as_uint(zv) | (tag + (1ull << 32)));
+                    if (publish && u == t && (k == nt - 1)) st_relaxed_gpu_u64(pa.hs.zt + (iter & 1) * (long long)zcount + e, (unsigned long long)__float_as_uint(zv) | (tag + (1ull << 32)));
                 }
             }
         }

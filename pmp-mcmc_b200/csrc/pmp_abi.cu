@@ -785,7 +785,7 @@ static int try_run_persistent(pmp_ctx* c, int64_t iters) {
     const bool hs = env_int("PMP_HANDOFF", 1) != 0;   // flag-in-data hand-offs (default) or release/acquire counters
     if (hs && (rc = ensure_handoff(c, &pa.hs))) return rc;
     // flat tree: a node is state + alpha * z(node) — the acceptance publishes the accepted state and every reader derives its nodes (Handoff::state)
-    pa.derive = hs && c->cfg.tree == PMP_TREE_FLAT && c->cfg.dim == 3 && n_sweep >= ntiles && env_int("PMP_DERIVE_NODES", 1);
+    pa.derive = hs && (c->cfg.tree == PMP_TREE_FLAT || c->cfg.tree == PMP_TREE_BINARY) && c->cfg.dim == 3 && n_sweep >= ntiles && ntiles <= 16 && env_int("PMP_DERIVE_NODES", 1);
     void* kargs[] = {&pa};
     const void* fn;
 #define PMP_SINGLE_FN(ALGO) (hs ? (const void*)chain_persistent_kernel<ALGO, true> : (const void*)chain_persistent_kernel<ALGO, false>)

@@ -8,9 +8,11 @@ import pmp_mcmc_b200 as pm
 from pmp_mcmc_b200 import _lib as L
 from conftest import synthetic_linear
 c = pm.Context(0)
-for n, P, scale in ((100000, 1024, 1000.0), (100000, 2048, 1000.0), (100000, 100, 1000.0), (500, 1024, 10.0), (500, 4, 10.0)):
+for n, P, scale in ((100000, 1024, 1000.0), (100000, -1024, 1000.0), (100000, 2048, 1000.0), (100000, 100, 1000.0), (500, 1024, 10.0), (500, 4, 10.0)):
     x, y = synthetic_linear(n)
-    c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.01, scale=scale)
+    if P > 0: c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_CUDA, alpha=0.01, scale=scale)
+    else:     # P < 0: the binary prefetch tree of 100000_PMP.cu (table rule as shipped), |P| = 2^depth nodes
+        c.configure(L.TREE_BINARY, depth=(-P).bit_length() - 1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_TABLE, draw=L.DRAW_CUDA, alpha=0.01, scale=scale, flags=L.FLAG_QUIRK_TABLE_CONST)
     c.set_data_linear(x, y)
     for derive in (0, 1):
         os.environ["PMP_DERIVE_NODES"] = str(derive)

@@ -145,9 +145,10 @@ def test_headline_shape_co_scheduled_equals_solo():
         c.close()
 
 
-@pytest.mark.parametrize("P,n", [(1024, 20000), (37, 5000), (4, 500), (2048, 3000), (130, 64)])
-def test_state_only_handoff_equals_node_handoff(P, n, monkeypatch):
-    """Flat trees in the persistent kernels: the acceptance publishes the accepted state and every reader derives its nodes (Handoff::state, DESIGN 4.0) —
+@pytest.mark.parametrize("tree,P,n", [("FLAT", 1024, 20000), ("FLAT", 37, 5000), ("FLAT", 4, 500), ("FLAT", 2048, 3000), ("FLAT", 130, 64),
+                                      ("PSP", 1024, 20000), ("PSP", 2048, 3000), ("PSP", 8, 500), ("PSP", 256, 64), ("TABLE", 1024, 5000)])
+def test_state_only_handoff_equals_node_handoff(tree, P, n, monkeypatch):
+    """Flat and binary trees in the persistent kernels: the acceptance publishes the accepted state and every reader derives its nodes (Handoff::state, DESIGN 4.0) —
     the traces, the draws, the log-weights and the nodes left behind must equal those of the hand-off that publishes every node (PMP_DERIVE_NODES=0),
     across launch boundaries and for a co-scheduled launch of one chain (chain_persistent_multi_kernel takes the same path for K = 1)."""
     import pmp_mcmc_b200 as pm
@@ -158,7 +159,13 @@ def test_state_only_handoff_equals_node_handoff(P, n, monkeypatch):
     for mode in ("0", "1", "multi"):
         monkeypatch.setenv("PMP_DERIVE_NODES", "0" if mode == "0" else "1")
         c = pm.Context(0)
-        c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_PYTHON, alpha=0.02, scale=max(n / 100.0, 1.0))
+        if tree == "FLAT":
+            c.configure(L.TREE_FLAT, b=P, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_MP, draw=L.DRAW_PYTHON, alpha=0.02, scale=max(n / 100.0, 1.0))
+        elif tree == "PSP":          # binary prefetch tree: a node is the state plus the increments of its ancestors
+            c.configure(L.TREE_BINARY, depth=P.bit_length() - 1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_PSP, draw=L.DRAW_PYTHON, alpha=0.02, scale=max(n / 100.0, 1.0))
+        else:                        # the 100000_PMP.cu shape (bench.py pmp_tree block)
+            c.configure(L.TREE_BINARY, depth=P.bit_length() - 1, dim=3, target=L.TARGET_LINEAR_GAUSS, algo=L.ALGO_TABLE, draw=L.DRAW_CUDA, alpha=0.02, scale=max(n / 100.0, 1.0),
+                        flags=L.FLAG_QUIRK_TABLE_CONST)
         c.set_data_linear(x, y); c.set_state([0.5, 1.0, 1.5]); c.seed(11, 0)
         c.trace_config(200, what)
         if mode == "multi":
