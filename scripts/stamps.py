@@ -21,6 +21,7 @@ for n, P in ((100000, 1024), (500, 4), (500, 1024)):
     print("  sweep CTA0 phases (cycles): start→stage_issued %d →nodes_built %d →data_landed %d →compute_done %d →flushed %d" % tuple(np.diff(sw_clk)))
     print("  sweep CTA0 start→end (globaltimer ns): %d" % (sw_ns[5] - sw_ns[0]))
     print("  accept phases (cycles): start→lt %d →logw %d →max/exp %d →scan %d →draws %d →state/trace %d" % tuple(np.diff(ac_clk)))
+    print("  accept post (cycles, stamp 6 -> 7): %d ; whole acceptance cycle pre -> end of post: %d" % (v[39] - v[38], v[39] - v[32]))
     print("  accept start→end ns: %d ; sweep CTA0 end → accept start ns: %d" % (ac_ns[6] - ac_ns[0], ac_ns[0] - sw_ns[5]))
     print("  sweep CTA0 start → accept end ns: %d" % (ac_ns[6] - sw_ns[0]))
     print("  [persistent] accept: wait_begin→(arrive seen)→body start %d cyc ; body end→released %d cyc ; sweep CTA0: wait %d, props %d, compute %d, flush %d, fence+arrive %d cyc" % (
