@@ -65,17 +65,26 @@ def load_peaks():
         return {}
 
 
+def torch_device_index():
+    import torch
+    return torch.cuda.current_device()
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.first = 0                      # rows before mark() belong to the warm-up (the sampler is started early: nvidia-smi takes ~100 ms to come up)
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -89,10 +98,11 @@ class ClockSampler(threading.Thread):
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
@@ -321,7 +331,10 @@ def extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps):
     del X
     ctx.set_state(theta0); ctx.seed(1, 0)
     ctx.trace_config(2 + steps, L.TRACE_NEXT)
+    sampler = ClockSampler(torch_device_index())
+    sampler.start()
     ctx.run(1)                                                   # warm-up iteration
+    sampler.mark()
     ms = []
     for _ in range(steps):
         ms.append(max_over_ranks(ctx.run_timed(1)[0]))
@@ -330,6 +343,7 @@ def extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps):
     sweep_s = 1e30
     for _ in range(2):                                           # best of two: a single sweep right after the timed iterations is at the mercy of the power state
         t0 = time.perf_counter(); ctx.loglik(read=False); ctx.sync(); sweep_s = min(sweep_s, max_over_ranks(time.perf_counter() - t0))
+    fc_clocks = sampler.summary()                                # seconds of tensor-core work at full power: this is where sw_power_cap shows
     lt = ctx.loglik()
     P = 1 << FC_DEPTH
     it_s = float(np.mean(ms)) * 1e-3
@@ -338,7 +352,7 @@ def extra_fc(L, pdist, ctx, world, rank, max_over_ranks, peaks, steps):
     mode = os.environ.get("PMP_FC_MODE", "delta")
     return {"workload": "FC 784-512-256-128-10, n=%d rows sharded over %d rank(s), P=%d nodes (binary tree D=%d), alpha=1e-4, theta0=%s" % (n, world, P, FC_DEPTH, theta_src),
             "value": P / it_s, "unit": UNIT, "iters_per_sec": 1.0 / it_s, "ms_per_iter": it_s * 1e3, "sweep_ms": sweep_s * 1e3, "accepted": [int(v) for v in nxt],
-            "logtarget_range": [float(lt.min()), float(lt.max())], "contraction": mode,
+            "logtarget_range": [float(lt.min()), float(lt.max())], "contraction": mode, "clocks": fc_clocks,
             "roofline": {"bound": "tensor", "achieved": alg / sweep_s / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": alg / sweep_s / 1e12 / peak,
                          "achieved_whole_iteration": alg / it_s / 1e12, "frac_whole_iteration": alg / it_s / 1e12 / peak,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus" if peaks else "fallback 1383.9 x n_gpus",
@@ -435,11 +449,12 @@ def main():
 
     # ---- ONE chain, device-resident: inputs already in HBM, CUDA events on the ctx stream, max over ranks (`value`) ------------
     ctx.set_state([1, 1, 1]); ctx.seed(2024, 0)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         ctx.l2_flush(); ctx.run(iters)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()                          # clocks / throttle reasons of the timed region only
     launches0 = ctx.launch_count()
     step_ms = []
     for _ in range(args.steps):
