@@ -44,7 +44,17 @@ __global__ void hmc_begin_kernel(const float* __restrict__ theta_parent, const f
         const float4 th = __ldg(reinterpret_cast<const float4*>(theta_parent) + i), g = __ldg(reinterpret_cast<const float4*>(grad) + i);
         float4 p0;
         if (p_init) p0 = reinterpret_cast<const float4*>(p_init)[i];
-        else {
+        else if (((idx0 + 4ull * i) & 1ull) == 0) {       // four consecutive elements from an even index = the four words of TWO Philox blocks (stream_u64: block idx >> 1, word idx & 1)
+            const uint64_t blk = (idx0 + 4ull * i) >> 1;
+            uint32_t c0[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)iter, ((uint32_t)(iter >> 32) & 0x00FFFFFFu) | ((uint32_t)STREAM_MOMENTUM << 24)};
+            uint32_t c1[4] = {(uint32_t)(blk + 1), (uint32_t)((blk + 1) >> 32), c0[2], c0[3]};
+            philox4x32_10(c0, (uint32_t)seed, (uint32_t)(seed >> 32));
+            philox4x32_10(c1, (uint32_t)seed, (uint32_t)(seed >> 32));
+            p0.x = __fmul_rn((float)det_norm_ppf(u64_to_open((uint64_t)c0[1] << 32 | c0[0])), p_scale);
+            p0.y = __fmul_rn((float)det_norm_ppf(u64_to_open((uint64_t)c0[3] << 32 | c0[2])), p_scale);
+            p0.z = __fmul_rn((float)det_norm_ppf(u64_to_open((uint64_t)c1[1] << 32 | c1[0])), p_scale);
+            p0.w = __fmul_rn((float)det_norm_ppf(u64_to_open((uint64_t)c1[3] << 32 | c1[2])), p_scale);
+        } else {
             p0.x = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i), p_scale);
             p0.y = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i + 1), p_scale);
             p0.z = __fmul_rn((float)stream_normal(seed, iter, STREAM_MOMENTUM, idx0 + 4ull * i + 2), p_scale);
