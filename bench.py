@@ -70,6 +70,9 @@ def torch_device_index():
     return torch.cuda.current_device()
 
 
+NCU_CHAIN_DRAM_BYTES = 914688 + 7936          # dram__bytes_read.sum + dram__bytes_write.sum of one chain_persistent_kernel launch (profiles/r2_chain_ncu_full_summary.txt)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
 
@@ -565,8 +568,8 @@ def main():
     kernel = ("chain_persistent_multi_kernel<MP> with one chain (sharded rows, in-kernel NVLink exchange; one launch per step)" if world > 1
               else "chain_persistent_kernel<MP> (one launch per step)")
     achieved = flops_per_iter / iter_s / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "traffic_note": "not captured in this run; ncu --set full of this launch: profiles/ (dram read+write ~0.9 MB per launch: the dataset is read once and then lives in shared memory)",
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": (NCU_CHAIN_DRAM_BYTES if world == 1 else None),
+                "traffic_note": "from profiles/r2_chain_ncu_full_summary.txt, not this run: one ncu --set full capture of this kernel (200 iterations in the launch) read 914 688 B and wrote 7 936 B of DRAM; it does not grow with the iteration count (the dataset, 0.8 MB, is read once and then lives in shared memory), so per launch it is ~1.1x the algorithmic 816 KB of ONE iteration and ~0.001x the algorithmic bytes of the 1000-iteration step",
                 "peak_source": "measured in this run by pmp_fp32_peak (FFMA/FFMA2 microbenchmark); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "note": "the sweep is bound by FP32 issue (3 lane-ops per node-point pair), not by HBM (0.8 MB, L2/shared-memory resident) nor by the tensor pipe; see DESIGN.md 4",
                 "kernel": kernel, "kernel_us": iter_s * 1e6 * iters, "flops_per_launch": flops_per_iter * iters,
