@@ -206,3 +206,22 @@ def test_glm_oracle_against_scipy():
     lg = o.loglik_glm_f64(X, yr, thg, "gauss", scale=8.0)
     refg = np.array([stats.norm(X @ t[:-1], t[-1]).logpdf(yr).sum() for t in thg]) / 8.0
     np.testing.assert_allclose(lg, refg, rtol=1e-12)
+
+
+def test_binary_tree_ancestors_split_by_tile():
+    """The index arithmetic behind the state-only hand-off for binary trees (chain_persistent.cuh): node 128 t + i is the state plus the increments
+    of its ancestors in creation order (accept.cuh for_each_ancestor: anc = node & (2^(l+1) - 1) for every set bit l, ascending), and that list is
+    [low-bit prefixes of i, in tile 0] + [element i of the tiles whose index is a low-bit prefix of t, t itself last] — so a sweep CTA needs the
+    normals of 1 + popcount(t) tiles."""
+    PT = 128
+    for depth in (1, 3, 7, 8, 10, 11):
+        P = 1 << depth
+        for node in range(P):
+            want = [node & ((2 << l) - 1) for l in range(depth) if (node >> l) & 1]
+            t, i = divmod(node, PT)
+            got = [i & ((2 << l) - 1) for l in range(7) if (i >> l) & 1]                      # tile 0, list entry 0
+            tiles = [0] + [t & ((2 << l) - 1) for l in range(4) if (t >> l) & 1]              # the CTA's tile list (kernel: tiles[])
+            got += [tiles[k] * PT + i for k in range(1, len(tiles))]                          # element i of list entry k
+            assert got == want, (depth, node, got, want)
+            assert len(tiles) == 1 + bin(t).count("1") <= 5
+            assert tiles[-1] == t
