@@ -1,4 +1,4 @@
-"""Single chain (pmp_run, flat MP tree): the acceptance publishing the accepted state only (PMP_DERIVE_NODES=1, default) against publishing every node (=0).
+"""Single chain (pmp_run; flat MP trees and the binary prefetch tree of 100000_PMP.cu): the acceptance publishing the accepted state only (PMP_DERIVE_NODES=1, default) against publishing every node (=0).
 Prints microseconds per iteration and the SHA-256 of a 400-iteration trace in both modes (must be equal)."""
 import hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
